@@ -1,0 +1,18 @@
+"""
+gpp_b200 (directory ``ground-plane-polling_b200``): B200-native ground-plane polling.
+
+The one hot path of arangesh/Ground-Plane-Polling -- the per-detection search over the road-plane database
+(keras_retinanet_3D/layers/fit_road_planes.py) plus the pose recovery that consumes it
+(keras_retinanet_3D/bin/run_network.py:137-247) -- as hand-written CUDA for sm_100a behind the reference's
+own call surface.  Import as ``import gpp_b200`` (root-level alias) or
+``importlib.import_module('ground-plane-polling_b200')``.
+"""
+from . import _lib  # noqa: F401
+from .layers import fit_road_planes as _frp_module  # noqa: F401
+from .layers.fit_road_planes import (FitRoadPlanes, PlanePoller, fit_road_planes, fit_road_planes_dlpack,  # noqa: F401
+                                     fit_road_planes_torch, get_poller)
+from .utils import synthetic  # noqa: F401
+from .utils import pose  # noqa: F401
+from .utils.pose import recover_pose, recover_pose_torch  # noqa: F401
+
+__version__ = '0.1.0'

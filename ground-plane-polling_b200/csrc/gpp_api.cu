@@ -1,0 +1,443 @@
+// libgpp C ABI (include/gpp.h): handle, plane-database upload + on-device normalisation, the host and
+// device entry points of fit_road_planes, measurement helpers.  No CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gpp.h"
+#include "gpp_internal.h"
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+namespace gpp {
+int set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+}  // namespace gpp
+
+using gpp::set_error;
+
+#define GPP_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return set_error(GPP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                                    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// plane normalisation, fit_road_planes.py:75-77 (once per database instead of once per call)
+// ---------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void normalise_planes_kernel(const float *__restrict__ raw, int n, typename E::T4 *__restrict__ out) {
+    typedef typename E::T T;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float4 r = reinterpret_cast<const float4 *>(raw)[j];
+    T p[4] = {T(r.x), T(r.y), T(r.z), T(r.w)};
+    const T dir = -gpp::tf_sign(p[1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = E::mul(p[i], dir);
+    const T rho = E::sqrt(E::add(E::add(E::mul(p[0], p[0]), E::mul(p[1], p[1])), E::mul(p[2], p[2])));
+    typename E::T4 o;
+    o.x = E::div(p[0], rho);
+    o.y = E::div(p[1], rho);
+    o.z = E::div(p[2], rho);
+    o.w = E::div(p[3], rho);
+    out[j] = o;
+}
+
+static uint64_t content_hash(const void *data, size_t bytes) {
+    const uint64_t *w = static_cast<const uint64_t *>(data);
+    size_t n = bytes / 8;
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t x;
+        memcpy(&x, w + i, 8);
+        h ^= x;
+        h *= 0xD6E8FEB86659FD93ull;
+        h ^= h >> 32;
+    }
+    const unsigned char *tail = static_cast<const unsigned char *>(data) + 8 * n;
+    for (size_t i = 0; i < bytes - 8 * n; ++i) {
+        h ^= tail[i];
+        h *= 0x100000001B3ull;
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpp_version(void) { return GPP_VERSION; }
+const char *gpp_last_error(void) { return g_last_error.c_str(); }
+
+int gpp_create(int device, gpp_handle **out) {
+    if (!out) return set_error(GPP_EINVAL, "gpp_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(GPP_ENODEV, "gpp_create: no CUDA device (%s); libgpp has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return set_error(GPP_EINVAL, "gpp_create: device %d out of range [0, %d)", device, count);
+    cudaDeviceProp prop;
+    GPP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(GPP_ENODEV, "gpp_create: device %d is sm_%d%d; libgpp is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(GPP_ECUDA, "gpp_create: cudaSetDevice(%d) failed", device);
+    gpp_handle *h = new (std::nothrow) gpp_handle();
+    if (!h) return set_error(GPP_ENOMEM, "gpp_create: out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < gpp_handle::kStreams; ++i) {
+        e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            gpp_destroy(h);
+            return set_error(GPP_ECUDA, "gpp_create: cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        }
+    }
+    e = cudaEventCreate(&h->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_stop);
+    if (e != cudaSuccess) {
+        gpp_destroy(h);
+        return set_error(GPP_ECUDA, "gpp_create: cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
+    int rc = gpp::configure_kernels(h);
+    if (rc != GPP_OK) {
+        gpp_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return GPP_OK;
+}
+
+int gpp_destroy(gpp_handle *h) {
+    if (!h) return GPP_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->d_raw);
+    cudaFree(h->d_planes32);
+    cudaFree(h->d_planes64);
+    for (int i = 0; i < gpp_handle::kStreams; ++i) {
+        h->stage[i].release();
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    for (auto &p : h->chunk_events) {
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    delete h;
+    return GPP_OK;
+}
+
+static int ensure_plane_capacity(gpp_handle *h, int n) {
+    if (n <= h->cap_planes) return GPP_OK;
+    cudaFree(h->d_raw);
+    cudaFree(h->d_planes32);
+    cudaFree(h->d_planes64);
+    h->d_raw = nullptr;
+    h->d_planes32 = nullptr;
+    h->d_planes64 = nullptr;
+    h->cap_planes = 0;
+    h->n_planes = 0;
+    GPP_CUDA(cudaMalloc(&h->d_raw, sizeof(float) * 4 * (size_t)n));
+    GPP_CUDA(cudaMalloc(&h->d_planes32, sizeof(float4) * (size_t)n));
+    GPP_CUDA(cudaMalloc(&h->d_planes64, sizeof(double4) * (size_t)n));
+    h->cap_planes = n;
+    return GPP_OK;
+}
+
+static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
+    const int threads = 128, blocks = (n + threads - 1) / threads;
+    normalise_planes_kernel<gpp::ExactF32><<<blocks, threads, 0, s>>>(h->d_raw, n, h->d_planes32);
+    normalise_planes_kernel<gpp::ExactF64><<<blocks, threads, 0, s>>>(h->d_raw, n, h->d_planes64);
+    h->launches += 2;
+    GPP_CUDA(cudaGetLastError());
+    return GPP_OK;
+}
+
+int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes) {
+    if (!h || !planes || n_planes <= 0) return set_error(GPP_EINVAL, "gpp_set_planes: bad argument");
+    const size_t bytes = sizeof(float) * 4 * (size_t)n_planes;
+    const uint64_t hash = content_hash(planes, bytes);
+    if (h->n_planes == n_planes && h->planes_hash == hash && h->planes_hash_valid) return GPP_OK;
+    DeviceGuard guard(h->device);
+    int rc = ensure_plane_capacity(h, n_planes);
+    if (rc) return rc;
+    cudaStream_t s = h->streams[0];
+    // all earlier work of this handle that may still read the old database must be done
+    GPP_CUDA(cudaDeviceSynchronize());
+    GPP_CUDA(cudaMemcpyAsync(h->d_raw, planes, bytes, cudaMemcpyHostToDevice, s));
+    rc = normalise_on(h, n_planes, s);
+    if (rc) return rc;
+    GPP_CUDA(cudaStreamSynchronize(s));
+    h->n_planes = n_planes;
+    h->planes_hash = hash;
+    h->planes_hash_valid = true;
+    return GPP_OK;
+}
+
+int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, void *stream) {
+    if (!h || !d_planes || n_planes <= 0) return set_error(GPP_EINVAL, "gpp_set_planes_device: bad argument");
+    DeviceGuard guard(h->device);
+    if (n_planes > h->cap_planes) GPP_CUDA(cudaDeviceSynchronize());
+    int rc = ensure_plane_capacity(h, n_planes);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GPP_CUDA(cudaMemcpyAsync(h->d_raw, d_planes, sizeof(float) * 4 * (size_t)n_planes, cudaMemcpyDeviceToDevice, s));
+    rc = normalise_on(h, n_planes, s);
+    if (rc) return rc;
+    h->n_planes = n_planes;
+    h->planes_hash_valid = false;
+    return GPP_OK;
+}
+
+int gpp_num_planes(const gpp_handle *h) { return h ? h->n_planes : 0; }
+
+int gpp_get_normalised_planes(gpp_handle *h, float *out) {
+    if (!h || !out || h->n_planes <= 0) return set_error(GPP_EINVAL, "gpp_get_normalised_planes: no planes set");
+    DeviceGuard guard(h->device);
+    GPP_CUDA(cudaDeviceSynchronize());
+    GPP_CUDA(cudaMemcpy(out, h->d_planes32, sizeof(float4) * (size_t)h->n_planes, cudaMemcpyDeviceToHost));
+    return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fit: device entries
+// ---------------------------------------------------------------------------------------------------
+static int check_fit_args(const gpp_handle *h, const void *boxes, const void *dims, const void *orient,
+                          const void *pinv, int B, int D, const void *kp, const void *kpl, const void *res,
+                          const char *who) {
+    if (!h) return set_error(GPP_EINVAL, "%s: handle is NULL", who);
+    if (B < 0 || D < 0) return set_error(GPP_EINVAL, "%s: negative size B=%d D=%d", who, B, D);
+    if (h->n_planes <= 0) return set_error(GPP_EINVAL, "%s: no plane database set (call gpp_set_planes)", who);
+    if ((long long)B * D > 0 && (!boxes || !dims || !orient || !pinv || !kp || !kpl || !res))
+        return set_error(GPP_EINVAL, "%s: NULL array argument", who);
+    return GPP_OK;
+}
+
+int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                   const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                   int64_t *best_index, int mode, void *stream) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_device");
+    if (rc) return rc;
+    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST)
+        return set_error(GPP_EINVAL, "gpp_fit_device: mode %d (use gpp_fit_device_f64 for the FP64 mode)", mode);
+    if ((long long)B * D == 0) return GPP_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    gpp::PollArgs<float> a;
+    a.boxes = boxes; a.dims = dimensions; a.orient = orientations; a.pinv = P_inv;
+    a.planes = h->d_planes32; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
+    a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
+    a.best = reinterpret_cast<long long *>(best_index);
+    GPP_CUDA(cudaEventRecord(h->ev_start, s));
+    rc = gpp::launch_poll_f32(h, a, mode, s);
+    if (rc) return rc;
+    GPP_CUDA(cudaEventRecord(h->ev_stop, s));
+    h->timing_chunks = 0;
+    h->timing_single = true;
+    return GPP_OK;
+}
+
+int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimensions,
+                       const int32_t *orientations, const float *P_inv, int B, int D, double *keypoints,
+                       double *keyplanes, double *residuals, int64_t *best_index, void *stream) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_device_f64");
+    if (rc) return rc;
+    if ((long long)B * D == 0) return GPP_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    gpp::PollArgs<double> a;
+    a.boxes = boxes; a.dims = dimensions; a.orient = orientations; a.pinv = P_inv;
+    a.planes = h->d_planes64; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
+    a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
+    a.best = reinterpret_cast<long long *>(best_index);
+    GPP_CUDA(cudaEventRecord(h->ev_start, s));
+    rc = gpp::launch_poll_f64(h, a, s);
+    if (rc) return rc;
+    GPP_CUDA(cudaEventRecord(h->ev_stop, s));
+    h->timing_chunks = 0;
+    h->timing_single = true;
+    return GPP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// fit: host entries.  The image axis is cut into chunks that alternate between two streams, so the H2D
+// copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (fully asynchronous when
+// the caller's buffers are pinned).
+// ---------------------------------------------------------------------------------------------------
+int gpp::Staging::reserve(long long n_det, int n_img, bool f64) {
+    const size_t esz = f64 ? sizeof(double) : sizeof(float);
+    if (n_det <= cap_det && n_img <= cap_img && esz <= out_elem) return GPP_OK;
+    release();
+    GPP_CUDA(cudaMalloc(&boxes, sizeof(float) * 12 * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&dims, sizeof(float) * 3 * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&orient, sizeof(int32_t) * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&pinv, sizeof(float) * 12 * (size_t)n_img));
+    GPP_CUDA(cudaMalloc(&keypoints, esz * 12 * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&keyplanes, esz * 4 * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&residuals, esz * (size_t)n_det));
+    GPP_CUDA(cudaMalloc(&best, sizeof(long long) * (size_t)n_det));
+    cap_det = n_det;
+    cap_img = n_img;
+    out_elem = esz;
+    return GPP_OK;
+}
+
+void gpp::Staging::release() {
+    cudaFree(boxes); cudaFree(dims); cudaFree(orient); cudaFree(pinv);
+    cudaFree(keypoints); cudaFree(keyplanes); cudaFree(residuals); cudaFree(best);
+    boxes = dims = pinv = nullptr;
+    orient = nullptr;
+    keypoints = keyplanes = residuals = nullptr;
+    best = nullptr;
+    cap_det = 0; cap_img = 0; out_elem = 0;
+}
+
+template <class T>
+static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, const int32_t *orient,
+                         const float *pinv, int B, int D, T *keypoints, T *keyplanes, T *residuals,
+                         int64_t *best, int mode) {
+    const bool f64 = sizeof(T) == 8;
+    if ((long long)B * D == 0) return GPP_OK;
+    DeviceGuard guard(h->device);
+    // chunk size: enough hypotheses to fill the machine a few times over, at most kMaxChunkDet detections
+    const long long max_chunk_det = 65536;
+    int imgs_per_chunk = (int)(max_chunk_det / (D > 0 ? D : 1));
+    if (imgs_per_chunk < 1) imgs_per_chunk = 1;
+    if (imgs_per_chunk > B) imgs_per_chunk = B;
+    const int n_chunks = (B + imgs_per_chunk - 1) / imgs_per_chunk;
+    const int n_streams = n_chunks > 1 ? gpp_handle::kStreams : 1;
+    for (int i = 0; i < n_streams; ++i) {
+        int rc = h->stage[i].reserve((long long)imgs_per_chunk * D, imgs_per_chunk, f64);
+        if (rc) return rc;
+    }
+    while ((int)h->chunk_events.size() < n_chunks) {
+        cudaEvent_t a, b;
+        GPP_CUDA(cudaEventCreate(&a));
+        GPP_CUDA(cudaEventCreate(&b));
+        h->chunk_events.push_back(std::make_pair(a, b));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = c * imgs_per_chunk;
+        const int nb = (b0 + imgs_per_chunk <= B) ? imgs_per_chunk : (B - b0);
+        const long long m0 = (long long)b0 * D, nm = (long long)nb * D;
+        gpp::Staging &st = h->stage[c % n_streams];
+        cudaStream_t s = h->streams[c % n_streams];
+        GPP_CUDA(cudaMemcpyAsync(st.boxes, boxes + 12 * m0, sizeof(float) * 12 * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.dims, dims + 3 * m0, sizeof(float) * 3 * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.orient, orient + m0, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.pinv, pinv + 12 * (size_t)b0, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
+        gpp::PollArgs<T> a;
+        a.boxes = st.boxes; a.dims = st.dims; a.orient = st.orient; a.pinv = st.pinv;
+        a.planes = f64 ? (const void *)h->d_planes64 : (const void *)h->d_planes32;
+        a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = nm;
+        a.keypoints = static_cast<T *>(st.keypoints);
+        a.keyplanes = static_cast<T *>(st.keyplanes);
+        a.residuals = static_cast<T *>(st.residuals);
+        a.best = best ? st.best : nullptr;
+        GPP_CUDA(cudaEventRecord(h->chunk_events[c].first, s));
+        int rc = gpp::launch_poll(h, a, mode, s);
+        if (rc) return rc;
+        GPP_CUDA(cudaEventRecord(h->chunk_events[c].second, s));
+        GPP_CUDA(cudaMemcpyAsync(keypoints + 12 * m0, st.keypoints, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
+        GPP_CUDA(cudaMemcpyAsync(keyplanes + 4 * m0, st.keyplanes, sizeof(T) * 4 * nm, cudaMemcpyDeviceToHost, s));
+        GPP_CUDA(cudaMemcpyAsync(residuals + m0, st.residuals, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
+        if (best)
+            GPP_CUDA(cudaMemcpyAsync(best + m0, st.best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < n_streams; ++i) GPP_CUDA(cudaStreamSynchronize(h->streams[i]));
+    h->timing_chunks = n_chunks;
+    h->timing_single = false;
+    return GPP_OK;
+}
+
+extern "C" {
+
+int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                 const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                 int64_t *best_index, int mode) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_host");
+    if (rc) return rc;
+    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST)
+        return set_error(GPP_EINVAL, "gpp_fit_host: mode %d (use gpp_fit_host_f64 for the FP64 mode)", mode);
+    return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                                best_index, mode);
+}
+
+int gpp_fit_host_f64(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                     const float *P_inv, int B, int D, double *keypoints, double *keyplanes,
+                     double *residuals, int64_t *best_index) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_host_f64");
+    if (rc) return rc;
+    return fit_host_impl<double>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                                 best_index, GPP_MODE_F64);
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gpp_last_kernel_ms(gpp_handle *h, float *ms) {
+    if (!h || !ms) return set_error(GPP_EINVAL, "gpp_last_kernel_ms: bad argument");
+    DeviceGuard guard(h->device);
+    float total = 0.f;
+    if (h->timing_single) {
+        GPP_CUDA(cudaEventSynchronize(h->ev_stop));
+        GPP_CUDA(cudaEventElapsedTime(&total, h->ev_start, h->ev_stop));
+    } else {
+        for (int c = 0; c < h->timing_chunks; ++c) {
+            float t = 0.f;
+            GPP_CUDA(cudaEventSynchronize(h->chunk_events[c].second));
+            GPP_CUDA(cudaEventElapsedTime(&t, h->chunk_events[c].first, h->chunk_events[c].second));
+            total += t;
+        }
+    }
+    *ms = total;
+    return GPP_OK;
+}
+
+int64_t gpp_launch_count(const gpp_handle *h) { return h ? h->launches : 0; }
+
+int gpp_debug_set_config(gpp_handle *h, int dets_per_warp, int ctas_per_sm) {
+    if (!h) return set_error(GPP_EINVAL, "gpp_debug_set_config: handle is NULL");
+    h->force_dpw = dets_per_warp;
+    h->force_ctas_per_sm = ctas_per_sm;
+    return GPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// Internal declarations shared by the libgpp translation units (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <utility>
+#include <vector>
+
+#include "gpp_poll.cuh"
+
+namespace gpp {
+
+int set_error(int code, const char *fmt, ...);
+
+// device-side staging buffers of one stream of the host entry point
+struct Staging {
+    float *boxes = nullptr, *dims = nullptr, *pinv = nullptr;
+    int32_t *orient = nullptr;
+    void *keypoints = nullptr, *keyplanes = nullptr, *residuals = nullptr;
+    long long *best = nullptr;
+    long long cap_det = 0;
+    int cap_img = 0;
+    size_t out_elem = 0;
+    int reserve(long long n_det, int n_img, bool f64);
+    void release();
+};
+
+}  // namespace gpp
+
+struct gpp_handle {
+    static constexpr int kStreams = 2;
+    int device = 0;
+    int sm_count = 0;
+    // plane database (device): raw upload, normalised fp32 (float4) and fp64 (double4) copies
+    float *d_raw = nullptr;
+    float4 *d_planes32 = nullptr;
+    double4 *d_planes64 = nullptr;
+    int n_planes = 0, cap_planes = 0;
+    uint64_t planes_hash = 0;
+    bool planes_hash_valid = false;
+    // host-entry plumbing
+    cudaStream_t streams[kStreams] = {nullptr, nullptr};
+    gpp::Staging stage[kStreams];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t> > chunk_events;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    int timing_chunks = 0;
+    bool timing_single = false;
+    int64_t launches = 0;
+    // launch configuration (filled by configure_kernels; the force_* fields are a tuning hook)
+    int force_dpw = 0, force_ctas_per_sm = 0;
+    int occ[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM for [mode][dpw-1]
+};
+
+namespace gpp {
+
+int configure_kernels(gpp_handle *h);
+int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s);
+int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a, cudaStream_t s);
+inline int launch_poll(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
+    return launch_poll_f32(h, a, mode, s);
+}
+inline int launch_poll(gpp_handle *h, const PollArgs<double> &a, int, cudaStream_t s) {
+    return launch_poll_f64(h, a, s);
+}
+
+}  // namespace gpp
+

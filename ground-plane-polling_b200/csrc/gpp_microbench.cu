@@ -1,0 +1,137 @@
+// FP32 CUDA-core pipe microbenchmarks: the roofline denominator of the polling kernel is the FP32 FMA
+// rate, which MEASURED_PEAKS.json does not carry, so bench.py measures it in the same run.
+// Every kernel keeps 16 independent dependency chains per thread in registers, runs with all SMs full
+// (8 warps x 4 CTAs per SM) and reports both wall-clock rate and operations per SM clock.
+#include "../../include/gpp.h"
+#include "gpp_internal.h"
+
+namespace gpp {
+
+constexpr int kChains = 16;
+constexpr int kInner = 64;    // unrolled repetitions per loop trip
+
+template <int KIND>
+__global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, float b, float *sink,
+                                                         long long *cycles) {
+    float acc[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) acc[i] = a * float(i + 1) + float(threadIdx.x) * 1e-3f;
+    float alu[4] = {a, b, a + b, a - b};
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int t = 0; t < trips; ++t) {
+#pragma unroll
+        for (int r = 0; r < kInner / 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) {
+                if (KIND == 0) {          // FFMA, three register operands
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+                } else if (KIND == 2) {   // FMUL then FADD, never contracted
+                    asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(a));
+                    asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(b));
+                } else if (KIND == 3) {   // MUFU.RCP
+                    asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(acc[i]));
+                } else if (KIND == 4) {   // MUFU.RSQ
+                    asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(acc[i]));
+                } else if (KIND == 5) {   // FFMA + one independent ALU-pipe op (FMNMX) per FFMA
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+                    asm volatile("max.f32 %0, %0, %1;" : "+f"(alu[i & 3]) : "f"(acc[(i + 8) & 15]));
+                } else if (KIND == 6) {   // sqrt.approx (MUFU.SQRT or MUFU.RSQ + FMUL)
+                    asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(acc[i]));
+                } else if (KIND == 8) {   // FFMA + MUFU.RCP 4:1
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+                    if ((i & 3) == 0) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(alu[(i >> 2) & 3]));
+                }
+            }
+            if (KIND == 1 || KIND == 7) { // packed f32x2: 8 register pairs
+                unsigned long long *p = reinterpret_cast<unsigned long long *>(acc);
+                unsigned long long pa, pb;
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep)
+#pragma unroll
+                    for (int i = 0; i < kChains / 2; ++i) {
+                        if (KIND == 1) {
+                            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb));
+                        } else {
+                            asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa));
+                            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+                        }
+                    }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float s = alu[0] + alu[1] + alu[2] + alu[3];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += acc[i];
+    if (s == 123.456f) sink[0] = s;                       // never true; keeps the chains alive
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int KIND>
+static int run_kind(gpp_handle *h, double ops_per_thread_trip, double *ops_per_s, float *ms,
+                    double *ops_per_clk_sm) {
+    const int ctas_per_sm = 4, threads = 256;
+    const int grid = h->sm_count * ctas_per_sm;
+    const int trips = 2000;
+    float *sink = nullptr;
+    long long *cyc = nullptr;
+    cudaError_t e = cudaMalloc(&sink, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&cyc, sizeof(long long) * grid);
+    if (e != cudaSuccess) { cudaFree(sink); return set_error(GPP_ECUDA, "microbench alloc: %s", cudaGetErrorString(e)); }
+    cudaStream_t s = h->streams[0];
+    float best = 1e30f;
+    std::vector<long long> hc(grid);
+    double best_cyc = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(h->ev_start, s);
+        microbench_kernel<KIND><<<grid, threads, 0, s>>>(trips, 0.999f, 1e-3f, sink, cyc);
+        cudaEventRecord(h->ev_stop, s);
+        e = cudaStreamSynchronize(s);
+        h->launches += 1;
+        if (e != cudaSuccess) break;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->ev_start, h->ev_stop);
+        cudaMemcpy(hc.data(), cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+        double mean = 0;
+        for (int i = 0; i < grid; ++i) mean += (double)hc[i];
+        mean /= grid;
+        if (rep > 0 && t < best) { best = t; best_cyc = mean; }
+    }
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "microbench: %s", cudaGetErrorString(e));
+    const double total_ops = ops_per_thread_trip * trips * (double)threads * grid;
+    if (ops_per_s) *ops_per_s = total_ops / (best * 1e-3);
+    if (ms) *ms = best;
+    // all CTAs of an SM are co-resident for the whole run, so per-SM ops / mean CTA cycles ~ ops per clock
+    if (ops_per_clk_sm) *ops_per_clk_sm = ops_per_thread_trip * trips * (double)threads * ctas_per_sm / best_cyc;
+    return GPP_OK;
+}
+
+}  // namespace gpp
+
+extern "C" int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm) {
+    if (!h) return gpp::set_error(GPP_EINVAL, "gpp_microbench: handle is NULL");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    const double per = gpp::kChains * (gpp::kInner / 4);
+    int rc;
+    switch (kind) {
+        case 0: rc = gpp::run_kind<0>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
+        case 1: rc = gpp::run_kind<1>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;       // 2 x 8 pairs x 2 lanes
+        case 2: rc = gpp::run_kind<2>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;       // mul + add
+        case 3: rc = gpp::run_kind<3>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
+        case 4: rc = gpp::run_kind<4>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
+        case 5: rc = gpp::run_kind<5>(h, per, ops_per_s, ms, ops_per_clk_sm); break;           // FFMA count only
+        case 6: rc = gpp::run_kind<6>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
+        case 7: rc = gpp::run_kind<7>(h, per * 4, ops_per_s, ms, ops_per_clk_sm); break;       // (mul+add) x 2 lanes x 2 reps
+        case 8: rc = gpp::run_kind<8>(h, per, ops_per_s, ms, ops_per_clk_sm); break;           // FFMA count only
+        default: rc = gpp::set_error(GPP_EINVAL, "gpp_microbench: unknown kind %d", kind);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}

@@ -1,0 +1,188 @@
+// 6-DoF pose recovery from the four selected 3-D key-points -- the step right after polling, inline in the
+// reference's driver loop (/root/reference/keras_retinanet_3D/bin/run_network.py:137-247).  Only the
+// branches that loop can reach are implemented (`outlier` is 2 for orientation 0/3 and 0 for 1/2,
+// :147-150): orientation 1 -> :167-177, 2 -> :178-188, 0 -> :204-214, 3 -> :237-247.
+// One thread per detection; float32 where the reference computes in float32 numpy, double for the
+// rotation-matrix -> Rodrigues-vector conversion (cv2.Rodrigues works in double: closest rotation by
+// SVD, then axis * angle).
+#include "../../include/gpp.h"
+#include "gpp_internal.h"
+
+namespace gpp {
+
+// Orthogonal polar factor U*Vt of a non-singular 3x3 matrix by scaled Newton iteration
+// Q <- (g*Q + Q^-T / g) / 2 -- equals the SVD projection cv2.Rodrigues applies before reading the axis.
+__device__ void polar_rotation(double Q[9]) {
+#pragma unroll 1
+    for (int iter = 0; iter < 24; ++iter) {
+        double C[9];   // cofactor matrix = det * Q^-T
+        C[0] = Q[4] * Q[8] - Q[5] * Q[7]; C[1] = Q[5] * Q[6] - Q[3] * Q[8]; C[2] = Q[3] * Q[7] - Q[4] * Q[6];
+        C[3] = Q[2] * Q[7] - Q[1] * Q[8]; C[4] = Q[0] * Q[8] - Q[2] * Q[6]; C[5] = Q[1] * Q[6] - Q[0] * Q[7];
+        C[6] = Q[1] * Q[5] - Q[2] * Q[4]; C[7] = Q[2] * Q[3] - Q[0] * Q[5]; C[8] = Q[0] * Q[4] - Q[1] * Q[3];
+        const double det = Q[0] * C[0] + Q[1] * C[1] + Q[2] * C[2];
+        if (!(fabs(det) > 0.0) || !isfinite(det)) return;
+        double nq = 0.0, nc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { C[i] /= det; nq += Q[i] * Q[i]; nc += C[i] * C[i]; }
+        const double g = sqrt(sqrt(nc / nq));
+        double delta = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double v = 0.5 * (g * Q[i] + C[i] / g);
+            delta += (v - Q[i]) * (v - Q[i]);
+            Q[i] = v;
+        }
+        if (delta < 1e-30) return;
+    }
+}
+
+// cv2.Rodrigues, matrix -> vector branch.  R row-major.
+__device__ void rodrigues_vec(const double Rin[9], double out[3]) {
+    double R[9];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { R[i] = Rin[i]; ok = ok && (R[i] > -100.0) && (R[i] < 100.0); }
+    if (!ok) { out[0] = out[1] = out[2] = 0.0; return; }         // checkRange(-100, 100) failure -> zeros
+    polar_rotation(R);
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) {
+            rx = ry = rz = 0.0;
+        } else {
+            double t;
+            t = (R[0] + 1.0) * 0.5; rx = sqrt(fmax(t, 0.0));
+            t = (R[4] + 1.0) * 0.5; ry = sqrt(fmax(t, 0.0)) * (R[1] < 0 ? -1.0 : 1.0);
+            t = (R[8] + 1.0) * 0.5; rz = sqrt(fmax(t, 0.0)) * (R[2] < 0 ? -1.0 : 1.0);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && ((R[5] > 0) != (ry * rz > 0))) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        const double vth = theta / (2.0 * s);
+        rx *= vth; ry *= vth; rz *= vth;
+    }
+    out[0] = rx; out[1] = ry; out[2] = rz;
+}
+
+__global__ void pose_kernel(const float *__restrict__ keypoints, const float *__restrict__ dims,
+                            const int32_t *__restrict__ orient, long long n, float *__restrict__ locations,
+                            float *__restrict__ angles, float *__restrict__ dims_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = orient[i];
+    if (o < 0 || o > 3) return;                                   // reference leaves such rows untouched
+    const float *kp = keypoints + 12 * i;
+    float Xl[3], Xm[3], Xr[3], Xt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Xl[k] = kp[k]; Xm[k] = kp[3 + k]; Xr[k] = kp[6 + k]; Xt[k] = kp[9 + k]; }
+    const float w = dims[3 * i + 1];
+    const bool use_r = (o == 1 || o == 2);                        // outlier == 0 -> (X_m, X_r, X_t)
+    const float *Xe = use_r ? Xr : Xl;
+    float tm[3], em[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { tm[k] = __fsub_rn(Xt[k], Xm[k]); em[k] = __fsub_rn(Xe[k], Xm[k]); }
+    const float h = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(tm[0], tm[0]), __fmul_rn(tm[1], tm[1])), __fmul_rn(tm[2], tm[2])));
+    const float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(em[0], em[0]), __fmul_rn(em[1], em[1])), __fmul_rn(em[2], em[2])));
+    // x_dir sign: o=1 (X_m-X_r)/l, o=2 (X_r-X_m)/l, o=0 (X_m-X_l)/l, o=3 (X_l-X_m)/l
+    const bool x_from_m = (o == 1 || o == 0);
+    float x[3], y[3], z[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dx = x_from_m ? __fsub_rn(Xm[k], Xe[k]) : __fsub_rn(Xe[k], Xm[k]);
+        x[k] = __fdiv_rn(dx, l);
+        y[k] = __fdiv_rn(__fsub_rn(Xm[k], Xt[k]), h);
+    }
+    z[0] = __fsub_rn(__fmul_rn(x[1], y[2]), __fmul_rn(x[2], y[1]));
+    z[1] = __fsub_rn(__fmul_rn(x[2], y[0]), __fmul_rn(x[0], y[2]));
+    z[2] = __fsub_rn(__fmul_rn(x[0], y[1]), __fmul_rn(x[1], y[0]));
+    // location: o=1 -, o=2 +, o=0 +, o=3 -
+    const bool plus = (o == 2 || o == 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float mid = __fdiv_rn(__fadd_rn(Xm[k], Xe[k]), 2.0f);
+        const float off = __fdiv_rn(__fmul_rn(z[k], w), 2.0f);
+        locations[3 * i + k] = plus ? __fadd_rn(mid, off) : __fsub_rn(mid, off);
+    }
+    const double R[9] = {(double)x[0], (double)y[0], (double)z[0], (double)x[1], (double)y[1], (double)z[1],
+                         (double)x[2], (double)y[2], (double)z[2]};   // columns x_dir, y_dir, z_dir
+    double rv[3];
+    rodrigues_vec(R, rv);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) angles[3 * i + k] = (float)rv[k];
+    dims_out[3 * i + 0] = h;
+    dims_out[3 * i + 1] = w;
+    dims_out[3 * i + 2] = l;
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+int gpp_pose_device(gpp_handle *h, const float *keypoints, const float *dimensions,
+                    const int32_t *orientations, long n, float *locations, float *angles,
+                    float *dimensions_out, void *stream) {
+    if (!h || n < 0) return gpp::set_error(GPP_EINVAL, "gpp_pose_device: bad argument");
+    if (n == 0) return GPP_OK;
+    if (!keypoints || !dimensions || !orientations || !locations || !angles || !dimensions_out)
+        return gpp::set_error(GPP_EINVAL, "gpp_pose_device: NULL array argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    gpp::pose_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        keypoints, dimensions, orientations, n, locations, angles, dimensions_out);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) return gpp::set_error(GPP_ECUDA, "pose_kernel launch: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+int gpp_pose_host(gpp_handle *h, const float *keypoints, const float *dimensions, const int32_t *orientations,
+                  long n, float *locations, float *angles, float *dimensions_out) {
+    if (!h || n < 0) return gpp::set_error(GPP_EINVAL, "gpp_pose_host: bad argument");
+    if (n == 0) return GPP_OK;
+    if (!keypoints || !dimensions || !orientations || !locations || !angles || !dimensions_out)
+        return gpp::set_error(GPP_EINVAL, "gpp_pose_host: NULL array argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    float *d = nullptr;
+    int32_t *d_or = nullptr;
+    const size_t nf = (size_t)n * (12 + 3 + 3 + 3 + 3);
+    cudaError_t e = cudaMalloc(&d, nf * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_or, (size_t)n * sizeof(int32_t));
+    int rc = GPP_OK;
+    if (e == cudaSuccess) {
+        float *d_kp = d, *d_dims = d + 12 * (size_t)n, *d_loc = d_dims + 3 * (size_t)n,
+              *d_ang = d_loc + 3 * (size_t)n, *d_dout = d_ang + 3 * (size_t)n;
+        cudaStream_t s = h->streams[0];
+        e = cudaMemcpyAsync(d_kp, keypoints, sizeof(float) * 12 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dims, dimensions, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_or, orientations, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s);
+        // rows with an orientation outside 0..3 keep whatever the caller's output buffers hold
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_loc, locations, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ang, angles, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dout, dimensions_out, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) rc = gpp_pose_device(h, d_kp, d_dims, d_or, n, d_loc, d_ang, d_dout, s);
+        if (e == cudaSuccess && rc == GPP_OK) {
+            e = cudaMemcpyAsync(locations, d_loc, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(angles, d_ang, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dimensions_out, d_dout, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+    }
+    cudaFree(d);
+    cudaFree(d_or);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (rc != GPP_OK) return rc;
+    if (e != cudaSuccess) return gpp::set_error(GPP_ECUDA, "gpp_pose_host: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+}  // extern "C"

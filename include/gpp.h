@@ -1,0 +1,136 @@
+/*
+ * libgpp -- B200-native ground-plane polling, C ABI.
+ *
+ * This is the drop-in boundary for the one hot path of arangesh/Ground-Plane-Polling: the per-detection
+ * search over the road-plane database.  The reference has no FFI for this path (it is a TensorFlow graph
+ * built by keras_retinanet_3D/layers/fit_road_planes.py:49-139 and run inside
+ * Model.predict_on_batch, keras_retinanet_3D/bin/run_network.py:110); the entry points below are what a
+ * ctypes binding of that function needs, and each one cites the reference interface it replaces.
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch / numpy types; row-major (C order) dense arrays;
+ *   - every function returns 0 on success, a GPP_E* code otherwise; gpp_last_error() gives the text
+ *     (thread-local);
+ *   - the caller owns every buffer; the library keeps no host pointer past the call; the device copy of
+ *     the plane database is owned by the handle;
+ *   - a handle is bound to one CUDA device and is not thread-safe (one handle per thread/GPU);
+ *   - there is NO CPU fallback: without a usable sm_100 device gpp_create() fails.
+ */
+#ifndef GPP_H_
+#define GPP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPP_VERSION 100 /* 0.1.0 */
+
+enum {
+    GPP_OK = 0,
+    GPP_EINVAL = 1, /* bad argument (null pointer, negative size, unknown mode, no planes set) */
+    GPP_ECUDA = 2,  /* CUDA runtime error, text in gpp_last_error() */
+    GPP_ENODEV = 3, /* no CUDA device / not an sm_100 part */
+    GPP_ENOMEM = 4
+};
+
+/* Arithmetic mode of the per-hypothesis math (the selection semantics are identical in all modes).
+ *   EXACT  : IEEE fp32, round-to-nearest, no FMA contraction, correctly rounded div/sqrt, the op order of
+ *            oracle/fit_road_planes_ref.py -> bit-identical to the oracle (index, key-points, residual).
+ *   FAST   : fp32 with FMA contraction and MUFU reciprocal / square root for the SEARCH; the winner's
+ *            key-points / residual are then recomputed with the EXACT arithmetic.  May pick a different
+ *            plane only when two planes score within float rounding noise of each other.
+ *   F64    : the same search in IEEE fp64 (verify mode for near-ties); only through gpp_fit_*_f64.
+ */
+enum { GPP_MODE_EXACT = 0, GPP_MODE_FAST = 1, GPP_MODE_F64 = 2 };
+
+typedef struct gpp_handle gpp_handle;
+
+int gpp_version(void);
+const char *gpp_last_error(void);
+
+/* Create / destroy a polling context on CUDA device `device` (>= 0). */
+int gpp_create(int device, gpp_handle **out);
+int gpp_destroy(gpp_handle *h);
+
+/* Upload one road-plane database: `planes` is host memory, N x 4 floats [a, b, c, d] per row, RAW (as
+ * loaded from road_planes_database_*.mat, run_network.py:75, cast to float32 like the Keras feed does).
+ * The sign flip and unit-normal normalisation of fit_road_planes.py:75-77 run once on the device.
+ * Re-sending identical content is detected (64-bit content hash) and costs no upload, because every
+ * reference caller re-feeds the same database with every image (run_network.py:105,
+ * preprocessing/kitti.py:220).  Replaces the `planes` input tensor of FitRoadPlanes.call
+ * (fit_road_planes.py:152-163, models/retinanet.py:396). */
+int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes);
+/* Same, from a device pointer (stream-ordered on `stream`, no hash shortcut). */
+int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, void *stream);
+int gpp_num_planes(const gpp_handle *h);
+/* Copy the normalised database (N x 4 floats) back to host -- the table `keyplanes` rows are taken from. */
+int gpp_get_normalised_planes(gpp_handle *h, float *out);
+
+/* fit_road_planes(boxes, dimensions, orientations, P_inv, planes) -> [keypoints, keyplanes, residuals]
+ * (fit_road_planes.py:49-61) for B images x D detections against the database set with gpp_set_planes.
+ *   boxes        B*D*12 floats (x1,y1,x2,y2,xl,yl,xm,ym,xr,yr,xt,yt)
+ *   dimensions   B*D*3  floats (h,w,l)
+ *   orientations B*D    int32  (class 0..3; -1 = padding row, processed like any other row)
+ *   P_inv        B*4*3  floats (pseudo-inverse of the scaled projection matrix, run_network.py:57-58)
+ *   keypoints    B*D*4*3 floats out   (X_l, X_m, X_r, X_t)
+ *   keyplanes    B*D*1*4 floats out   (normalised, sign-flipped winning plane)
+ *   residuals    B*D     floats out   (masked residual of the winner / 6)
+ *   best_index   B*D     int64  out, may be NULL (extension: the argmin itself, fit_road_planes.py:119)
+ * Host entry: pointers are host memory (pinned memory makes the copies asynchronous); the call returns
+ * when the outputs are complete.  Host<->device copies are chunked and overlapped with the kernel. */
+int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                 const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                 int64_t *best_index, int mode);
+
+/* Device entry (the torch / DLPack path): all pointers are device memory on the handle's device; the
+ * kernels are enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
+ * without synchronising. */
+int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                   const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                   int64_t *best_index, int mode, void *stream);
+
+/* FP64 verify mode: same inputs (float32, promoted exactly), search and outputs in double. */
+int gpp_fit_host_f64(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                     const float *P_inv, int B, int D, double *keypoints, double *keyplanes,
+                     double *residuals, int64_t *best_index);
+int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimensions,
+                       const int32_t *orientations, const float *P_inv, int B, int D, double *keypoints,
+                       double *keyplanes, double *residuals, int64_t *best_index, void *stream);
+
+/* 6-DoF pose recovery from the four selected key-points -- the inline loop of run_network.py:137-247
+ * (reachable branches only: orientation 1,2 use X_m,X_r,X_t; 0,3 use X_l,X_m,X_t).
+ *   keypoints    n*12 floats, dimensions n*3 floats (h,w,l), orientations n int32
+ *   locations    n*3 floats out, angles n*3 floats out (Rodrigues vector of [x_dir y_dir z_dir]),
+ *   dimensions_out n*3 floats out (h and l overwritten by the measured key-point distances)
+ * Rows whose orientation is outside 0..3 are left untouched, like the reference's np.empty_like rows. */
+int gpp_pose_host(gpp_handle *h, const float *keypoints, const float *dimensions, const int32_t *orientations,
+                  long n, float *locations, float *angles, float *dimensions_out);
+int gpp_pose_device(gpp_handle *h, const float *keypoints, const float *dimensions,
+                    const int32_t *orientations, long n, float *locations, float *angles,
+                    float *dimensions_out, void *stream);
+
+/* Measurement helpers (bench.py): time of the last gpp_fit_* polling kernel(s) in milliseconds, measured
+ * with CUDA events on the launching stream (valid after the stream has been synchronised); number of
+ * kernels launched by this handle so far. */
+int gpp_last_kernel_ms(gpp_handle *h, float *ms);
+int64_t gpp_launch_count(const gpp_handle *h);
+
+/* FP32 CUDA-core pipe microbenchmarks on the handle's device (the roofline denominator of this path):
+ * `kind` 0 = FFMA (3 register operands), 1 = packed FFMA2 (fma.rn.f32x2), 2 = FMUL+FADD uncontracted,
+ * 3 = MUFU.RCP, 4 = MUFU.RSQ, 5 = FFMA with one ALU-pipe FMNMX per FFMA (FFMAs counted),
+ * 6 = sqrt.approx, 7 = packed FMUL2+FADD2, 8 = FFMA with one MUFU.RCP per 4 FFMA (FFMAs counted).
+ * Returns operations per second (an FMA counts as ONE operation; x2 for FLOP), the duration of the best
+ * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
+int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
+
+/* Tuning hook (benchmarks only): force detections-per-warp (1 or 2, 0 = automatic) and resident CTAs per
+ * SM used to size the persistent grid (0 = occupancy maximum). */
+int gpp_debug_set_config(gpp_handle *h, int dets_per_warp, int ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPP_H_ */

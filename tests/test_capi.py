@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, exports every symbol include/gpp.h declares, and fails
+loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, 'include', 'gpp.h')) as f:
+        text = f.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gpp_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for must in ('gpp_create', 'gpp_destroy', 'gpp_set_planes', 'gpp_fit_host', 'gpp_fit_device',
+                 'gpp_fit_host_f64', 'gpp_fit_device_f64', 'gpp_pose_host', 'gpp_pose_device', 'gpp_last_error'):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(gpp):
+    lib = gpp._lib.load()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), 'libgpp.so does not export %s' % name
+        assert name in gpp._lib.SIGNATURES, 'no ctypes signature for %s' % name
+    assert lib.gpp_version() == 100
+
+
+def test_library_is_in_tree_and_sm100a(gpp):
+    path = gpp._lib.LIB_PATH
+    assert os.path.dirname(path) == os.path.join(ROOT, 'ground-plane-polling_b200')
+    assert os.path.exists(path)
+
+
+def test_python_surface_mirrors_the_reference(gpp):
+    import inspect
+    sig = inspect.signature(gpp.fit_road_planes)
+    assert list(sig.parameters)[:5] == ['boxes', 'dimensions', 'orientations', 'P_inv', 'planes']
+    layer = gpp.FitRoadPlanes()
+    shapes = layer.compute_output_shape([(2, 100, 12), (2, 100, 3), (2, 100), (2, 4, 3), (2, 10, 4)])
+    assert shapes == [(2, 100, 4, 3), (2, 100, 1, 4), (2, 100)]
+    assert layer.compute_mask([1, 2, 3, 4, 5]) == [None] * 5
+    assert 'name' in layer.get_config()
+
+
+def test_no_cpu_fallback_without_a_gpu(gpp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    lib = gpp._lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.gpp_create(0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b'no CPU fallback' in lib.gpp_last_error()
+    import numpy as np
+    with pytest.raises(RuntimeError):
+        gpp.fit_road_planes(np.zeros((1, 1, 12), np.float32), np.ones((1, 1, 3), np.float32),
+                            np.zeros((1, 1), np.int32), np.zeros((1, 4, 3), np.float32),
+                            np.ones((3, 4), np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'ground-plane-polling_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                with open(os.path.join(base, f)) as fh:
+                    src = fh.read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), (base, f)
+                assert 'libgpp_oracle' not in src, (base, f)
