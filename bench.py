@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""
+bench.py -- ground-plane hypotheses/s (detections x planes) of the polling hot path on N x B200.
+
+    python bench.py --gpus N --steps K --warmup W              (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[3] = "C4": 4096 KITTI-size images x 100 synthetic
+detections x road_planes_database_22k (21634 planes) PER GPU (weak scaling: images are sharded, the database is
+replicated, there is no collective on the data path -- SURVEY.md section 8.5).  A step is one pass of the hot
+path over that batch.
+
+    value      whole-job hypotheses/s with the inputs already resident in HBM: sum over the K steps of the
+               polling kernel's CUDA-event time on its launching stream, max over ranks; L2 is flushed
+               between steps (the working set is smaller than L2)
+    e2e        the same metric through the public numpy-in/numpy-out call ``fit_road_planes`` (C ABI
+               ``gpp_fit_host``) from PINNED HOST buffers, host->device and device->host copies inside the
+               timed region, wall clock between barriers
+    roofline   FP32 CUDA-core bound (this path is neither HBM- nor tensor-bound: 0.006 B/hypothesis):
+               achieved = 148 algorithmic FLOP/hypothesis x hypotheses / kernel time;
+               peak = FFMA rate measured by libgpp's microbenchmark in this same run (MEASURED_PEAKS.json has no
+               FP32 entry), nominal 74.4 TFLOP/s beside it
+    cpu_baseline  the oracle port (numpy restatement of the reference graph) timed on this box's host cores
+               on a bounded sample of the same workload
+
+--impl reference times the reference's CPU implementation of the path: TensorFlow is not installable here,
+so it is the oracle port (numpy restatement, one process per host core over images), on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_ALG = 148.0                      # algorithmic FLOP per hypothesis, SURVEY.md section 8.4
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+METRIC = 'ground-plane hypotheses/sec (dets x planes)'
+UNIT = 'hypotheses/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='gpp', choices=['gpp', 'reference'])
+    ap.add_argument('--images', type=int, default=4096, help='images per GPU (C4: 4096)')
+    ap.add_argument('--dets', type=int, default=100)
+    ap.add_argument('--planes', default='22k', choices=['10', '100', '1k', '10k', '22k'])
+    ap.add_argument('--mode', default=os.environ.get('GPP_BENCH_MODE', 'exact'), choices=['exact', 'fast'])
+    ap.add_argument('--cpu-sample-images', type=int, default=0, help='images in the CPU-baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def load_planes(tag):
+    return np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_%s.npy' % tag))
+
+
+def make_workload(images, dets, planes, seed):
+    """Seeded synthetic KITTI-shaped detections.  A pool of 256 distinct images is
+    generated and tiled to `images` (generation is host-side numpy and not part of any timed region)."""
+    from gpp_b200.utils import synthetic
+    pool = min(images, 256)
+    boxes, dims, orient, P_inv = synthetic.synth_detections(pool, dets, planes, seed=seed)
+    rep = (images + pool - 1) // pool
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:images])  # noqa: E731
+    return tile(boxes), tile(dims), tile(orient), tile(P_inv.astype(np.float32))
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for l in rows:
+            f = [x.strip() for x in l.split(',')]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def _numpy_port_worker(job):
+    from oracle.fit_road_planes_ref import fit_road_planes_ref
+    boxes, dims, orient, P_inv, planes = job
+    fit_road_planes_ref(boxes, dims, orient, P_inv, planes)
+    return boxes.shape[0] * boxes.shape[1] * planes.shape[0]
+
+
+def cpu_numpy_port(boxes, dims, orient, P_inv, planes, procs):
+    """The oracle port (numpy restatement of fit_road_planes.py) over `procs` processes, one image per job."""
+    B = boxes.shape[0]
+    jobs = [(boxes[b:b + 1], dims[b:b + 1], orient[b:b + 1], P_inv[b:b + 1], planes) for b in range(B)]
+    t0 = time.time()
+    if procs <= 1:
+        hyp = sum(_numpy_port_worker(j) for j in jobs)
+    else:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(procs) as pool:
+            pool.map(_numpy_port_worker, jobs[:procs])          # untimed: worker start-up + imports
+            t0 = time.time()
+            hyp = sum(pool.map(_numpy_port_worker, jobs, chunksize=1))
+    return hyp, time.time() - t0
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    planes = load_planes(args.planes)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_img = args.cpu_sample_images or max(procs, 8)
+    boxes, dims, orient, P_inv = make_workload(n_img, args.dets, planes, seed=3)
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    times, hyp = [], 0
+    for i in range(args.warmup + args.steps):
+        h, dt = cpu_numpy_port(boxes, dims, orient, P_inv, planes, procs)
+        if i >= args.warmup:
+            times.append(dt)
+            hyp += h
+    total = sum(times)
+    value = hyp / total
+    sample = '%d images x %d detections x %d planes per step (bounded sample of the 4096-image C4 batch)' % (
+        n_img, args.dets, planes.shape[0])
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, planes),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample,
+                         'what': 'numpy restatement of keras_retinanet_3D/layers/fit_road_planes.py (TensorFlow is '
+                                 'not installable here), one process per host core over images',
+                         'host_cpu_count': cores},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, planes):
+    return {'workload': 'C4: %d images x %d detections x road_planes_database_%s (%d planes) per GPU, KITTI P2 '
+                        '1242x375 scaled 1333/1242' % (args.images, args.dets, args.planes, planes.shape[0]),
+            'images_per_gpu': args.images, 'detections_per_image': args.dets, 'planes': int(planes.shape[0]),
+            'mode': args.mode, 'sharding': 'images sharded, plane database replicated, no collective',
+            'l2': 'flushed between timed steps (256 MiB write); working set < L2'}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gpp_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the polling path has no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    planes = load_planes(args.planes)
+    N = int(planes.shape[0])
+    boxes, dims, orient, P_inv = make_workload(args.images, args.dets, planes, seed=3 + rank)
+    hyp_per_step = float(args.images) * args.dets * N
+    poller = gpp_b200.get_poller(local_rank)
+    poller.set_planes(planes)
+
+    # ---------------- FP32 peak (roofline denominator), measured in this run
+    ffma = poller.microbench(0)
+    peak_tflops = 2.0 * ffma['ops_per_s'] / 1e12
+
+    # ---------------- device-resident leg: `value`
+    tb, td = torch.from_numpy(boxes).to(dev), torch.from_numpy(dims).to(dev)
+    to, tp = torch.from_numpy(orient).to(dev), torch.from_numpy(P_inv).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def device_step():
+        flush.fill_(1)                                       # evict L2 (untimed: kernel time comes from events)
+        out = poller.fit_torch(tb, td, to, tp, mode=args.mode)
+        return out
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = poller.launch_count()
+    t_clock0 = time.time()
+    kernel_ms = []
+    barrier()
+    w0 = time.time()
+    for _ in range(args.steps):
+        device_step()
+        torch.cuda.synchronize()
+        kernel_ms.append(poller.last_kernel_ms())            # CUDA events around the kernel, launching stream
+    barrier()
+    wall_dev = time.time() - w0
+    t_clock1 = time.time()
+    launches = poller.launch_count() - launches0
+    dev_ms = max_over_ranks(sum(kernel_ms))
+    value = world * hyp_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---------------- end-to-end leg: public numpy API, pinned host buffers, copies inside the timed region
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    hb, hd, ho, hp = pinned(boxes), pinned(dims), pinned(orient), pinned(P_inv)
+    B, D = args.images, args.dets
+    outs_t = [torch.empty((B, D, 4, 3), dtype=torch.float32, pin_memory=True),
+              torch.empty((B, D, 1, 4), dtype=torch.float32, pin_memory=True),
+              torch.empty((B, D), dtype=torch.float32, pin_memory=True)]
+    outs = [t.numpy() for t in outs_t]
+    nb, nd, no, npi = hb.numpy(), hd.numpy(), ho.numpy(), hp.numpy()
+
+    def e2e_step():
+        gpp_b200.fit_road_planes(nb, nd, no, npi, planes, mode=args.mode, device=local_rank, out=outs)
+        return float(outs[2][0, 0])                          # the step's result is read on the host
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    e0 = time.time()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.time() - e0)
+    e2e_value = world * hyp_per_step * args.steps / e2e_s
+    h2d = int(nb.nbytes + nd.nbytes + no.nbytes + npi.nbytes)
+    d2h = int(sum(o.nbytes for o in outs))
+    clocks = sampler.stop(t_clock0, max(t_clock1, time.time()))
+
+    # ---------------- the other arithmetic mode, for context (kernel only, 3 steps)
+    other = 'fast' if args.mode == 'exact' else 'exact'
+    oms = []
+    for i in range(4):
+        poller.fit_torch(tb, td, to, tp, mode=other)
+        torch.cuda.synchronize()
+        if i:
+            oms.append(poller.last_kernel_ms())
+    other_value = world * hyp_per_step / (max_over_ranks(float(np.mean(oms))) * 1e-3)
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        n_img = args.cpu_sample_images or 8
+        h, dt = cpu_numpy_port(boxes[:n_img], dims[:n_img], orient[:n_img], P_inv[:n_img], planes, 1)
+        c_threads = c_oracle.max_threads()
+        c_img = min(args.images, max(16, 2 * c_threads))
+        t0 = time.time()
+        c_oracle.fit_road_planes_c(boxes[:c_img], dims[:c_img], orient[:c_img], P_inv[:c_img], planes)
+        c_dt = time.time() - t0
+        cpu = {'value': h / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+               'sample': '%d images x %d detections x %d planes (%.1f s)' % (n_img, D, N, dt),
+               'what': 'numpy restatement of the reference graph, single process',
+               'c_port_value': c_img * D * N / c_dt, 'c_port_cores': c_threads,
+               'c_port_sample': '%d images (%.1f s), fused C restatement, all host threads' % (c_img, c_dt),
+               'host_cpu_count': os.cpu_count()}
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        achieved = W_ALG * value / world / 1e12              # per-GPU TFLOP/s of algorithmic work
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, planes),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': 1e3 * e2e_s / args.steps,
+                    'api': 'gpp_b200.fit_road_planes (numpy in/out, pinned host buffers) -> gpp_fit_host'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak_tflops, 'traffic': None,
+                         'peak_source': 'libgpp FFMA microbenchmark, same run (MEASURED_PEAKS.json has no FP32 entry)',
+                         'nominal_peak': NOMINAL_FP32_TFLOPS, 'frac_of_nominal': achieved / NOMINAL_FP32_TFLOPS,
+                         'flop_per_hypothesis': W_ALG, 'kernel': 'gpp::poll_kernel<%s>' % args.mode,
+                         'kernel_ms_per_launch': ms_per_step},
+            'cpu_baseline': cpu,
+            'other_mode': {'mode': other, 'value': other_value, 'unit': UNIT},
+            'wall_ms_per_step_device_leg': 1e3 * wall_dev / args.steps,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

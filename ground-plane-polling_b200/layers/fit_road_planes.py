@@ -71,9 +71,10 @@ class PlanePoller(object):
         return out
 
     # ------------------------------------------------------------------ numpy entry
-    def fit(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False):
+    def fit(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False, out=None):
         """fit_road_planes against the resident database.  Returns [keypoints (B, D, 4, 3),
-        keyplanes (B, D, 1, 4), residuals (B, D)] float32 (float64 in mode 'f64') [+ best index int64]."""
+        keyplanes (B, D, 1, 4), residuals (B, D)] float32 (float64 in mode 'f64') [+ best index int64].
+        ``out`` may hold preallocated C-contiguous result arrays (e.g. pinned host memory) to write into."""
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in _lib.MODES:
             raise ValueError('unknown mode %r (expected one of %s)' % (mode, sorted(_lib.MODES)))
@@ -91,10 +92,21 @@ class PlanePoller(object):
         if P_inv.shape != (B, 4, 3):
             raise ValueError('P_inv must have shape (%d, 4, 3), got %r' % (B, P_inv.shape))
         out_t = np.float64 if mode == 'f64' else np.float32
-        keypoints = np.empty((B, D, 4, 3), out_t)
-        keyplanes = np.empty((B, D, 1, 4), out_t)
-        residuals = np.empty((B, D), out_t)
-        best = np.empty((B, D), np.int64) if return_index else None
+        if out is not None:
+            want = [((B, D, 4, 3), out_t), ((B, D, 1, 4), out_t), ((B, D), out_t)] + \
+                   ([((B, D), np.int64)] if return_index else [])
+            if len(out) != len(want):
+                raise ValueError('out must hold %d arrays' % len(want))
+            for a, (shape, dt) in zip(out, want):
+                if not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != dt or not a.flags['C_CONTIGUOUS']:
+                    raise ValueError('out array must be C-contiguous %s %r' % (np.dtype(dt).name, shape))
+            keypoints, keyplanes, residuals = out[0], out[1], out[2]
+            best = out[3] if return_index else None
+        else:
+            keypoints = np.empty((B, D, 4, 3), out_t)
+            keyplanes = np.empty((B, D, 1, 4), out_t)
+            residuals = np.empty((B, D), out_t)
+            best = np.empty((B, D), np.int64) if return_index else None
         if mode == 'f64':
             rc = self._lib.gpp_fit_host_f64(self._h, _lib.ptr(boxes), _lib.ptr(dimensions), _lib.ptr(orientations),
                                             _lib.ptr(P_inv), B, D, _lib.ptr(keypoints), _lib.ptr(keyplanes),
@@ -235,7 +247,8 @@ def _plane_groups(planes, B):
     return groups
 
 
-def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False, device=None):
+def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False, device=None,
+                    out=None):
     """ Identify 3D keypoints and keyplane for each detection (drop-in for fit_road_planes.py:49).
     Args
         boxes                 : (num_batch, num_dets, 12) boxes in (x1, y1, x2, y2, xl, yl, xm, ym, xr, yr, xt, yt) format.
@@ -249,7 +262,8 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
         keyplanes is shaped (num_batch, num_dets, 1, 4) and contains the fitted road plane corresponding to each detection.
         residuals is shaped (num_batch, num_dets) and contains the best 'error of fit' corresponding to the keyplane.
     Extensions (do not change the default return list): ``mode`` 'exact' | 'fast' | 'f64',
-    ``return_index`` appends the winning plane index (int64), ``device`` picks the GPU.
+    ``return_index`` appends the winning plane index (int64), ``device`` picks the GPU, ``out`` is a list of
+    preallocated result arrays (single shared database only).
     """
     poller = get_poller(device)
     boxes = np.asarray(boxes)
@@ -259,7 +273,9 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     groups = _plane_groups(planes, B)
     if len(groups) == 1:
         poller.set_planes(groups[0][2])
-        return poller.fit(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index)
+        return poller.fit(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index, out=out)
+    if out is not None:
+        raise ValueError('out= is only supported with one plane database shared by the batch')
     dimensions, orientations, P_inv = np.asarray(dimensions), np.asarray(orientations), np.asarray(P_inv)
     parts = []
     for b0, b1, db in groups:
