@@ -146,6 +146,7 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->d_raw);
     cudaFree(h->d_planes32);
     cudaFree(h->d_planes64);
+    cudaFree(h->d_pairs);
     for (int i = 0; i < gpp_handle::kStreams; ++i) {
         h->stage[i].release();
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -165,6 +166,8 @@ static int ensure_plane_capacity(gpp_handle *h, int n) {
     cudaFree(h->d_raw);
     cudaFree(h->d_planes32);
     cudaFree(h->d_planes64);
+    cudaFree(h->d_pairs);
+    h->d_pairs = nullptr;
     h->d_raw = nullptr;
     h->d_planes32 = nullptr;
     h->d_planes64 = nullptr;
@@ -173,6 +176,7 @@ static int ensure_plane_capacity(gpp_handle *h, int n) {
     GPP_CUDA(cudaMalloc(&h->d_raw, sizeof(float) * 4 * (size_t)n));
     GPP_CUDA(cudaMalloc(&h->d_planes32, sizeof(float4) * (size_t)n));
     GPP_CUDA(cudaMalloc(&h->d_planes64, sizeof(double4) * (size_t)n));
+    GPP_CUDA(cudaMalloc(&h->d_pairs, 32 * (size_t)((n + 63) / 64) * 32));
     h->cap_planes = n;
     return GPP_OK;
 }
@@ -183,7 +187,9 @@ static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
     normalise_planes_kernel<gpp::ExactF64><<<blocks, threads, 0, s>>>(h->d_raw, n, h->d_planes64);
     h->launches += 2;
     GPP_CUDA(cudaGetLastError());
-    return GPP_OK;
+    h->n_planes = n;
+    h->n_pairs_padded = ((n + 63) / 64) * 32;
+    return gpp::build_pairs(h, s);
 }
 
 int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes) {
@@ -192,11 +198,11 @@ int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes) {
     const uint64_t hash = content_hash(planes, bytes);
     if (h->n_planes == n_planes && h->planes_hash == hash && h->planes_hash_valid) return GPP_OK;
     DeviceGuard guard(h->device);
+    // all earlier work of this handle that may still read the old database must be done
+    GPP_CUDA(cudaDeviceSynchronize());
     int rc = ensure_plane_capacity(h, n_planes);
     if (rc) return rc;
     cudaStream_t s = h->streams[0];
-    // all earlier work of this handle that may still read the old database must be done
-    GPP_CUDA(cudaDeviceSynchronize());
     GPP_CUDA(cudaMemcpyAsync(h->d_raw, planes, bytes, cudaMemcpyHostToDevice, s));
     rc = normalise_on(h, n_planes, s);
     if (rc) return rc;

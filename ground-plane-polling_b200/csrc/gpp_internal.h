@@ -7,7 +7,7 @@
 #include <utility>
 #include <vector>
 
-#include "gpp_poll.cuh"
+#include "gpp_poll2.cuh"
 
 namespace gpp {
 
@@ -36,6 +36,8 @@ struct gpp_handle {
     float *d_raw = nullptr;
     float4 *d_planes32 = nullptr;
     double4 *d_planes64 = nullptr;
+    unsigned long long *d_pairs = nullptr;   // pair-interleaved fp32 copy, padded to 64 planes (gpp_poll2.cuh)
+    int n_pairs_padded = 0;
     int n_planes = 0, cap_planes = 0;
     uint64_t planes_hash = 0;
     bool planes_hash_valid = false;
@@ -49,13 +51,14 @@ struct gpp_handle {
     int64_t launches = 0;
     // launch configuration (filled by configure_kernels; the force_* fields are a tuning hook)
     int force_dpw = 0, force_ctas_per_sm = 0;
-    int occ[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM for [mode][dpw-1]
+    int occ[3] = {0, 0, 0};                      // resident CTAs per SM for [mode]
 };
 
 namespace gpp {
 
 int configure_kernels(gpp_handle *h);
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s);
+int build_pairs(gpp_handle *h, cudaStream_t s);
 int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a, cudaStream_t s);
 inline int launch_poll(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
     return launch_poll_f32(h, a, mode, s);

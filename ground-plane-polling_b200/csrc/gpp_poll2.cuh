@@ -1,0 +1,443 @@
+// Packed-pair polling kernel (fp32 modes).
+//
+// Blackwell's FP32 pipe executes packed two-wide instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 /
+// FMUL2 / FFMA2): a packed add or multiply delivers two IEEE-rounded results per issue slot and a packed FMA
+// two FMAs per slot (measured: profiles/r01a_probe_microbench_sweep.json).  The polling kernel is issue-slot
+// bound, so every lane evaluates TWO planes per iteration (the pair (2p, 2p+1) of a pair-interleaved copy of
+// the database) against its warp's detection; per-detection constants are plain 32-bit registers that the
+// packed instructions broadcast (SASS operand form `R.F32`), abs/neg fold into operand modifiers.
+//
+// Same algorithm as gpp_poll.cuh (fit_road_planes.py:86-119), plus one specialisation: as soon as the warp
+// has seen a plane with all six votes, max-votes is known to be 6 for good, and "votes == 6" becomes
+// "max_k |r_k| <= 0.7" (NaN-ignoring max keeps the reference's NaN-votes rule), which replaces the vote
+// counting by three FMNMX3.
+#pragma once
+#include "gpp_poll.cuh"
+
+namespace gpp {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------ packed f32x2 primitives
+struct f2 {
+    u64 v;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 bc(float x) { return pk(x, x); }      // broadcast operand (folds to R.F32)
+__device__ __forceinline__ float lo(f2 a) {
+    float l, h;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a.v));
+    return l;
+}
+__device__ __forceinline__ float hi(f2 a) {
+    float l, h;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a.v));
+    return h;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return pk(-lo(a), -hi(a)); }
+__device__ __forceinline__ f2 abs2(f2 a) { return pk(fabsf(lo(a)), fabsf(hi(a))); }
+
+// per-half scalar ops
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {      // NaN-ignoring (IEEE maxNum)
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// ------------------------------------------------------------------ packed policies
+struct PackExact {
+    static constexpr bool kExact = true;
+    typedef ExactF32 Scalar;
+    // a*b + c, a*b - c with two roundings (the canonical, FMA-free arithmetic)
+    static __device__ __forceinline__ f2 madd(f2 a, f2 b, f2 c) { return add2(mul2(a, b), c); }
+    static __device__ __forceinline__ f2 div(f2 a, f2 b) {
+        return pk(__fdiv_rn(lo(a), lo(b)), __fdiv_rn(hi(a), hi(b)));
+    }
+    static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(__fsqrt_rn(lo(a)), __fsqrt_rn(hi(a))); }
+};
+
+struct PackFast {
+    static constexpr bool kExact = false;
+    typedef FastF32 Scalar;
+    static __device__ __forceinline__ f2 madd(f2 a, f2 b, f2 c) { return fma2(a, b, c); }
+    static __device__ __forceinline__ f2 rcp(f2 a) { return pk(rcp_approx(lo(a)), rcp_approx(hi(a))); }
+    static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(sqrt_approx(lo(a)), sqrt_approx(hi(a))); }
+};
+
+// per-detection constants of the packed kernels (warp-uniform scalars)
+struct DetConst {
+    float dl[3], dm[3], dr[3], dt[3];
+    float td[6];
+    float T;           // |d_t|^2 (fast formulation only)
+};
+
+struct PairResult {
+    f2 r[6];           // signed residuals dist_k - target_k (abs is applied by the consumers)
+    f2 zc;             // z_dir_check
+};
+
+__device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, float b2, bool exact) {
+    // (a0*b0 + a1*b1) + a2*b2, exact: three multiplies and two adds; fast: multiply + two FMAs
+    if (exact) return add2(add2(mul2(a0, bc(b0)), mul2(a1, bc(b1))), mul2(a2, bc(b2)));
+    return fma2(a2, bc(b2), fma2(a1, bc(b1), mul2(a0, bc(b0))));
+}
+
+// ---- EXACT: the canonical op order of oracle/fit_road_planes_ref.py, two planes at a time
+__device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
+                                          PairResult &out, f2 X[4][3]) {
+    const float *rays[3] = {D.dl, D.dm, D.dr};
+    const f2 nd = neg2(d4);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f2 t = dot3p(n0, n1, n2, rays[k][0], rays[k][1], rays[k][2], true);
+        f2 s = abs2(PackExact::div(nd, t));
+        X[k][0] = mul2(bc(rays[k][0]), s);
+        X[k][1] = mul2(bc(rays[k][1]), s);
+        X[k][2] = mul2(bc(rays[k][2]), s);
+    }
+    f2 ax = sub2(X[0][0], X[1][0]), az = sub2(X[0][2], X[1][2]);
+    f2 bx = sub2(X[2][0], X[1][0]), bz = sub2(X[2][2], X[1][2]);
+    out.zc = sub2(mul2(az, bx), mul2(ax, bz));
+    const float *dt = D.dt;
+    f2 c0 = sub2(mul2(n1, bc(dt[2])), mul2(n2, bc(dt[1])));
+    f2 c1 = sub2(mul2(n2, bc(dt[0])), mul2(n0, bc(dt[2])));
+    f2 c2 = sub2(mul2(n0, bc(dt[1])), mul2(n1, bc(dt[0])));
+    f2 p0 = sub2(mul2(bc(dt[1]), c2), mul2(bc(dt[2]), c1));
+    f2 p1 = sub2(mul2(bc(dt[2]), c0), mul2(bc(dt[0]), c2));
+    f2 p2 = sub2(mul2(bc(dt[0]), c1), mul2(bc(dt[1]), c0));
+    f2 num = add2(add2(mul2(p0, X[1][0]), mul2(p1, X[1][1])), mul2(p2, X[1][2]));
+    f2 den = add2(add2(mul2(p0, n0), mul2(p1, n1)), mul2(p2, n2));
+    f2 q = PackExact::div(num, den);
+    X[3][0] = sub2(X[1][0], mul2(q, n0));
+    X[3][1] = sub2(X[1][1], mul2(q, n1));
+    X[3][2] = sub2(X[1][2], mul2(q, n2));
+    const int pa[6] = {1, 0, 1, 0, 0, 2}, pb[6] = {3, 1, 2, 2, 3, 3};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        f2 dx = sub2(X[pa[k]][0], X[pb[k]][0]), dy = sub2(X[pa[k]][1], X[pb[k]][1]);
+        f2 dz = sub2(X[pa[k]][2], X[pb[k]][2]);
+        f2 dist = PackExact::sqrt(add2(add2(mul2(dx, dx), mul2(dy, dy)), mul2(dz, dz)));
+        out.r[k] = sub2(dist, bc(D.td[k]));
+    }
+}
+
+// ---- FAST: FMA contraction, MUFU reciprocal / square root, and algebra that is exact in real arithmetic:
+//   perp = d_t x (n x d_t) = n |d_t|^2 - d_t (n.d_t);  perp.n = |d_t|^2 - (n.d_t)^2 for a unit normal;
+//   X_l - X_t = (X_l - X_m) + q n,  X_r - X_t = (X_r - X_m) + q n,  |X_m - X_t| = |q|.
+__device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
+                                          PairResult &out, f2 X[4][3]) {
+    const float *rays[3] = {D.dl, D.dm, D.dr};
+    const f2 ad = abs2(d4);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f2 t = dot3p(n0, n1, n2, rays[k][0], rays[k][1], rays[k][2], false);
+        f2 s = mul2(ad, PackFast::rcp(abs2(t)));
+        X[k][0] = mul2(bc(rays[k][0]), s);
+        X[k][1] = mul2(bc(rays[k][1]), s);
+        X[k][2] = mul2(bc(rays[k][2]), s);
+    }
+    f2 a[3], b[3], c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        a[i] = sub2(X[0][i], X[1][i]);          // X_l - X_m
+        b[i] = sub2(X[2][i], X[1][i]);          // X_r - X_m
+        c[i] = sub2(a[i], b[i]);                // X_l - X_r
+    }
+    out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
+    const float *dt = D.dt;
+    f2 u = dot3p(n0, n1, n2, dt[0], dt[1], dt[2], false);
+    f2 nu = neg2(u);
+    f2 p0 = fma2(bc(dt[0]), nu, mul2(n0, bc(D.T)));
+    f2 p1 = fma2(bc(dt[1]), nu, mul2(n1, bc(D.T)));
+    f2 p2 = fma2(bc(dt[2]), nu, mul2(n2, bc(D.T)));
+    f2 num = fma2(p2, X[1][2], fma2(p1, X[1][1], mul2(p0, X[1][0])));
+    f2 den = fma2(nu, u, bc(D.T));
+    f2 q = mul2(num, PackFast::rcp(den));
+    f2 e[3], f[3];
+    e[0] = fma2(q, n0, a[0]); e[1] = fma2(q, n1, a[1]); e[2] = fma2(q, n2, a[2]);     // X_l - X_t
+    f[0] = fma2(q, n0, b[0]); f[1] = fma2(q, n1, b[1]); f[2] = fma2(q, n2, b[2]);     // X_r - X_t
+#define GPP_SQN(v) fma2(v[2], v[2], fma2(v[1], v[1], mul2(v[0], v[0])))
+    out.r[0] = sub2(abs2(q), bc(D.td[0]));
+    out.r[1] = sub2(PackFast::sqrt(GPP_SQN(a)), bc(D.td[1]));
+    out.r[2] = sub2(PackFast::sqrt(GPP_SQN(b)), bc(D.td[2]));
+    out.r[3] = sub2(PackFast::sqrt(GPP_SQN(c)), bc(D.td[3]));
+    out.r[4] = sub2(PackFast::sqrt(GPP_SQN(e)), bc(D.td[4]));
+    out.r[5] = sub2(PackFast::sqrt(GPP_SQN(f)), bc(D.td[5]));
+#undef GPP_SQN
+    (void)X;
+}
+
+// residual sum ((((|r0|+|r1|)+|r2|)+|r3|)+|r4|)+|r5| for both planes of the pair
+__device__ __forceinline__ f2 resid_sum(const PairResult &h) {
+    f2 s = add2(abs2(h.r[0]), abs2(h.r[1]));
+    s = add2(s, abs2(h.r[2]));
+    s = add2(s, abs2(h.r[3]));
+    s = add2(s, abs2(h.r[4]));
+    s = add2(s, abs2(h.r[5]));
+    return s;
+}
+__device__ __forceinline__ int votes_of(float r0, float r1, float r2, float r3, float r4, float r5) {
+    const float thr = 0.7f;   // where(greater(|r|, thr), 0, 1): NaN is not greater -> a vote (:31)
+    return int(!(fabsf(r0) > thr)) + int(!(fabsf(r1) > thr)) + int(!(fabsf(r2) > thr)) +
+           int(!(fabsf(r3) > thr)) + int(!(fabsf(r4) > thr)) + int(!(fabsf(r5) > thr));
+}
+__device__ __forceinline__ float rmax_of(float r0, float r1, float r2, float r3, float r4, float r5) {
+    float m = max3f(fabsf(r0), fabsf(r1), fabsf(r2));
+    m = max3f(m, fabsf(r3), fabsf(r4));
+    return fmaxf(m, fabsf(r5));
+}
+
+// state of a lane once max-votes is known to be 6: best = min residual over {all six votes, z-check passes}
+struct LaneBest {
+    float bestR;
+    int bestIdx;
+    __device__ __forceinline__ void update6(float rmax, float zc, float R, int j) {
+        const bool better = !(rmax > 0.7f) && !(zc < 0.0f) && (R < bestR);
+        bestR = better ? R : bestR;
+        bestIdx = better ? j : bestIdx;
+    }
+};
+
+template <class T>
+struct PollArgs2 {
+    const float *boxes, *dims, *pinv;
+    const int32_t *orient;
+    const u64 *pairs;            // pair-interleaved normalised DB: per pair {a0,a1,b0,b1,c0,c1,d0,d1}
+    const float4 *planes;        // plain normalised DB (N x float4), for the epilogue
+    int n_planes;                // N
+    int n_pairs_padded;          // multiple of 32 (database padded to 64 planes with copies of the last)
+    int dets_per_image;
+    long long n_det;
+    T *keypoints, *keyplanes, *residuals;
+    long long *best;
+};
+
+// kTile planes per smem tile (multiple of 64), one detection per warp.
+template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
+    constexpr int kTilePairs = kTile / 2;
+    constexpr uint32_t kPairBytes = 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ulonglong2 *tiles = reinterpret_cast<ulonglong2 *>(smem_raw);             // 2 x ulonglong2 per pair
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(kPairBytes) * kStages * kTilePairs);
+    uint64_t *empty_bar = full_bar + kStages;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = args.n_planes;
+    const int NP = args.n_pairs_padded;
+    const int n_tiles = (NP + kTilePairs - 1) / kTilePairs;
+    const long long n_groups = (args.n_det + kWarps - 1) / kWarps;
+    const long long my_groups = (n_groups > blockIdx.x) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_tiles = my_groups * n_tiles;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long it) {
+        const int s = int(it % kStages);
+        const int t = int(it % n_tiles);
+        const int cnt = min(kTilePairs, NP - t * kTilePairs);
+        const uint32_t bytes = uint32_t(cnt) * kPairBytes;
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tma_load_1d(reinterpret_cast<unsigned char *>(tiles) + size_t(s) * kTilePairs * kPairBytes,
+                    reinterpret_cast<const unsigned char *>(args.pairs) + size_t(t) * kTilePairs * kPairBytes, bytes,
+                    &full_bar[s]);
+    };
+    if (threadIdx.x == 0) {
+        const long long pre = total_tiles < kStages ? total_tiles : kStages;
+        for (long long it = 0; it < pre; ++it) issue(it);
+    }
+
+    long long it = 0;
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
+        const long long m = g * kWarps + warp;
+        const long long mm = m < args.n_det ? m : args.n_det - 1;
+        DetConst D;
+        {
+            Detection<ExactF32> det;
+            load_detection<ExactF32, ExactF32>(det, args.boxes + 12 * mm, args.dims + 3 * mm,
+                                               __ldg(args.orient + mm), args.pinv + 12 * (mm / args.dets_per_image));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
+            D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
+        }
+        LaneState<float> st;                 // general mode (max votes not yet known to be 6)
+        st.reset(FLT_MAX);
+        LaneBest b6;                         // M == 6 mode
+        b6.bestR = FLT_MAX; b6.bestIdx = 0;
+        bool m6 = false;
+
+        for (int t = 0; t < n_tiles; ++t, ++it) {
+            const int s = int(it % kStages);
+            mbar_wait(&full_bar[s], uint32_t((it / kStages) & 1));
+            const ulonglong2 *tile = tiles + size_t(s) * kTilePairs * 2;
+            const int rows = min(kTilePairs, NP - t * kTilePairs) >> 5;
+            const int base_pair = t * kTilePairs;
+            int r = 0;
+            if (!m6) {
+#pragma unroll 1
+                for (; r < rows; ++r) {
+                    const int p = (r << 5) + lane;
+                    const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
+                    PairResult h;
+                    f2 X[4][3];
+                    eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                    const f2 R = resid_sum(h);
+                    const int j = 2 * (base_pair + p);
+                    const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                    const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                    st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
+                    st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
+                    if ((r & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                        m6 = true;                               // warp-uniform decision
+                        ++r;
+                        break;
+                    }
+                }
+                if (m6) {
+                    // candidates found under a lower running max are masked from now on
+                    b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
+                    b6.bestIdx = st.bestIdx;
+                }
+            }
+#pragma unroll 1
+            for (; r < rows; ++r) {
+                const int p = (r << 5) + lane;
+                const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
+                PairResult h;
+                f2 X[4][3];
+                eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                const f2 R = resid_sum(h);
+                const int j = 2 * (base_pair + p);
+                b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                           lo(h.zc), lo(R), j);
+                b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
+                           hi(h.zc), hi(R), j + 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (threadIdx.x == 0 && it >= 1) {
+                const long long prev = it - 1;
+                if (prev + kStages < total_tiles) {
+                    mbar_wait(&empty_bar[prev % kStages], uint32_t((prev / kStages) & 1));
+                    issue(prev + kStages);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- epilogue: warp reduction, lazy first-masked search, exact recompute of the winner
+        int Mw;
+        float rbest;
+        int idx;
+        if (m6) {
+            Mw = 6;
+            rbest = b6.bestR;
+            idx = b6.bestIdx;
+        } else {
+            Mw = __reduce_max_sync(0xffffffffu, st.M);
+            rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
+            idx = st.bestIdx;
+        }
+        rbest = warp_min_first(rbest, idx);
+        const bool have_cand = rbest < FLT_MAX;
+        bool sentinel = false;
+        if (!(rbest < 100.0f)) {
+            int first_masked = -1;
+            for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
+                const int p = p0 + lane;                         // pair index; the padded DB covers it
+                const ulonglong2 v0 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p];
+                const ulonglong2 v1 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p + 1];
+                PairResult h;
+                f2 X[4][3];
+                eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                const bool mk0 = (2 * p < N) && ((V0 < Mw) || (lo(h.zc) < 0.0f));
+                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || (hi(h.zc) < 0.0f));
+                const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
+                if (b0 | b1) {
+                    const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
+                    const int f1 = b1 ? 2 * (p0 + __ffs(b1) - 1) + 1 : 0x7fffffff;
+                    first_masked = min(f0, f1);
+                }
+            }
+            if (first_masked >= 0) {
+                if (!have_cand || 100.0f < rbest || (100.0f == rbest && first_masked < idx)) {
+                    sentinel = true;
+                    idx = first_masked;
+                }
+            } else if (!have_cand) {
+                idx = 0;
+            }
+        }
+        if (m < args.n_det && lane == 0) {
+            const float4 pl = args.planes[idx];
+            Detection<ExactF32> de;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { de.dl[i] = D.dl[i]; de.dm[i] = D.dm[i]; de.dr[i] = D.dr[i]; de.dt[i] = D.dt[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) de.td[i] = D.td[i];
+            float X[4][3];
+            int V; float R; bool zneg;
+            hypothesis<ExactF32>(de, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            const float rr = sentinel ? 100.0f : R;
+            float *kp = args.keypoints + 12 * m;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) kp[3 * k + i] = X[k][i];
+            float *kpl = args.keyplanes + 4 * m;
+            kpl[0] = pl.x; kpl[1] = pl.y; kpl[2] = pl.z; kpl[3] = pl.w;
+            args.residuals[m] = __fdiv_rn(rr, 6.0f);
+            if (args.best) args.best[m] = idx;
+        }
+    }
+}
+
+}  // namespace gpp

@@ -126,7 +126,7 @@ int64_t gpp_launch_count(const gpp_handle *h);
  * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
 
-/* Tuning hook (benchmarks only): force detections-per-warp (1 or 2, 0 = automatic) and resident CTAs per
+/* Tuning hook (benchmarks only): reserved (ignored) and resident CTAs per
  * SM used to size the persistent grid (0 = occupancy maximum). */
 int gpp_debug_set_config(gpp_handle *h, int dets_per_warp, int ctas_per_sm);
 

@@ -48,18 +48,37 @@ def test_exact_mode_is_bit_identical_to_the_oracle(gpp, tag, B, D, seed):
     _assert_identical(got, want)
 
 
-def test_exact_mode_config3_slice_two_detections_per_warp(gpp, poller):
-    """Config 3 shape (64 x 100 x 10k) on the 2-detections-per-warp kernel, checked on every row."""
+def test_exact_mode_config3_full(gpp, poller):
+    """Config 3 shape (64 x 100 x 10k), every row checked; also with a forced 1-CTA-per-SM grid (longer
+    per-CTA tile streams, more ring wrap-arounds)."""
     planes = load_planes('10k')
     boxes, dims, orient, P_inv = synthetic.synth_detections(64, 100, planes, seed=33)
     want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
-    for dpw in (1, 2):
-        poller.debug_set_config(dets_per_warp=dpw)
+    for cps in (0, 1):
+        poller.debug_set_config(0, cps)
         try:
             got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='exact', return_index=True)
         finally:
             poller.debug_set_config(0, 0)
         _assert_identical(got, want)
+
+
+def test_max_votes_below_six_and_late_six(gpp):
+    """Detections whose maximum vote count stays below 6 (general path for the whole database) and
+    detections whose only 6-vote plane comes late (switch to the all-six-votes path mid-stream)."""
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(2, 100, planes, seed=34)
+    dims = dims.copy()
+    dims[0, :50, 1] *= 1.6                     # wrong widths: some polls can never vote -> max votes < 6
+    dims[1, :50, 0] *= 0.5
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='exact', return_index=True)
+    _assert_identical(got, want)
+    # a database whose good planes are at the very end
+    rev = planes[::-1].copy()
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, rev, return_index=True)
+    got = gpp.fit_road_planes(boxes, dims, orient, P_inv, rev, mode='exact', return_index=True)
+    _assert_identical(got, want)
 
 
 def test_f64_mode_matches_fp64_oracle(gpp):
