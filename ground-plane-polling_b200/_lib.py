@@ -44,6 +44,7 @@ SIGNATURES = {
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),
     'gpp_debug_set_config': (c_int, [c_void_p, c_int, c_int]),
+    'gpp_debug_scores': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _LIB = None

@@ -439,9 +439,44 @@ int gpp_last_kernel_ms(gpp_handle *h, float *ms) {
 
 int64_t gpp_launch_count(const gpp_handle *h) { return h ? h->launches : 0; }
 
-int gpp_debug_set_config(gpp_handle *h, int dets_per_warp, int ctas_per_sm) {
+int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
+                     int which, int32_t *votes, float *resid, int32_t *zneg) {
+    if (!h || !box12 || !dims3 || !pinv12 || !votes || !resid || !zneg || h->n_planes <= 0 || which < 0 || which > 2)
+        return set_error(GPP_EINVAL, "gpp_debug_scores: bad argument");
+    DeviceGuard guard(h->device);
+    const int n = h->n_planes;
+    float host_det[27];
+    memcpy(host_det, box12, 12 * sizeof(float));
+    memcpy(host_det + 12, dims3, 3 * sizeof(float));
+    memcpy(host_det + 15, pinv12, 12 * sizeof(float));
+    float *d_det = nullptr, *d_res = nullptr;
+    int32_t *d_int = nullptr;
+    cudaError_t e = cudaMalloc(&d_det, sizeof(host_det));
+    if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_int, sizeof(int32_t) * (2 * (size_t)n + 1));
+    int rc = GPP_OK;
+    if (e == cudaSuccess) {
+        cudaStream_t s = h->streams[0];
+        int32_t o = orientation;
+        e = cudaMemcpyAsync(d_det, host_det, sizeof(host_det), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_int + 2 * (size_t)n, &o, sizeof(o), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) rc = gpp::launch_scores(h, d_det, d_int + 2 * (size_t)n, which, d_int, d_res, d_int + n, s);
+        if (e == cudaSuccess && rc == GPP_OK) {
+            e = cudaMemcpyAsync(votes, d_int, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(zneg, d_int + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(resid, d_res, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+    }
+    cudaFree(d_det); cudaFree(d_res); cudaFree(d_int);
+    if (rc != GPP_OK) return rc;
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "gpp_debug_scores: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm) {
     if (!h) return set_error(GPP_EINVAL, "gpp_debug_set_config: handle is NULL");
-    h->force_dpw = dets_per_warp;
+    h->force_variant = variant;
     h->force_ctas_per_sm = ctas_per_sm;
     return GPP_OK;
 }

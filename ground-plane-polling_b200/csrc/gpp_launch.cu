@@ -3,6 +3,10 @@
 #include "../../include/gpp.h"
 #include "gpp_internal.h"
 
+#ifndef GPP_DEFAULT_VARIANT_FAST
+#define GPP_DEFAULT_VARIANT_FAST 1
+#endif
+
 namespace gpp {
 
 // CTA shape: 8 warps, 1024-plane tiles (32 KB fp32 pairs / 32 KB fp64), 3-stage TMA ring.
@@ -52,39 +56,126 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
 
 constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t);
 constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t);
-#define GPP_K_EXACT poll2_kernel<PackExact, kWarps, kTile32, kStages, GPP_MINB_EXACT>
-#define GPP_K_FAST poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MINB_FAST>
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
-#ifndef GPP_MINB_EXACT
-#define GPP_MINB_EXACT 2
-#endif
-#ifndef GPP_MINB_FAST
-#define GPP_MINB_FAST 2
-#endif
+
+// EXACT fp32 mode runs the scalar kernel (gpp_poll.cuh): ptxas 12.9 contracts a packed mul.rn.f32x2 feeding a
+// packed add.rn.f32x2 into FFMA2 even with explicit .rn (checked in SASS), which would break the FMA-free
+// canonical arithmetic, so the packed kernel is used for the FAST mode only.
+#define GPP_K_EXACT1 poll_kernel<ExactF32, kWarps, 1, kTile32, kStages>
+#define GPP_K_EXACT2 poll_kernel<ExactF32, kWarps, 2, kTile32, kStages>
+constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t);
+
+// FAST kernel variants: v = 0..2 <-> __launch_bounds__(256, 2 / 3 / 4) i.e. <= 128 / 80 / 64 registers
+typedef void (*Poll2Fn)(const PollArgs2<float>);
+static Poll2Fn fast_variant(int v) {
+    switch (v) {
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2>;
+        case 1: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 4>;
+    }
+}
 
 int configure_kernels(gpp_handle *h) {
     int rc;
-    if ((rc = configure_kernel(GPP_K_EXACT, kSmem2, &h->occ[0]))) return rc;
-    if ((rc = configure_kernel(GPP_K_FAST, kSmem2, &h->occ[1]))) return rc;
+    if ((rc = configure_kernel(GPP_K_EXACT1, kSmem1, &h->occ[0]))) return rc;
+    if ((rc = configure_kernel(GPP_K_EXACT2, kSmem1, &h->occ[1]))) return rc;
+    for (int v = 0; v < 3; ++v)
+        if ((rc = configure_kernel(fast_variant(v), kSmem2, &h->occ2[v]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64, kSmem64, &h->occ[2]))) return rc;
     return GPP_OK;
 }
 
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
-    PollArgs2<float> b;
-    b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
-    b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
-    b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
-    b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
-    const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
     if (mode == GPP_MODE_FAST) {
-        GPP_K_FAST<<<(unsigned)grid_for(h, n_groups, h->occ[1]), kWarps * 32, kSmem2, s>>>(b);
+        PollArgs2<float> b;
+        b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
+        b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
+        b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
+        b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
+        const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+        int v = GPP_DEFAULT_VARIANT_FAST;
+        if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
+        fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
     } else {
-        GPP_K_EXACT<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem2, s>>>(b);
+        // two detections per warp once every SM has several groups to chew on
+        const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
+        const bool two = a.n_det >= 4 * resident;
+        if (two) {
+            const long long n_groups = (a.n_det + 2 * kWarps - 1) / (2 * kWarps);
+            GPP_K_EXACT2<<<(unsigned)grid_for(h, n_groups, h->occ[1]), kWarps * 32, kSmem1, s>>>(a);
+        } else {
+            const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(a);
+        }
     }
     h->launches += 1;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll2_kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll kernel launch: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// test hook: per-hypothesis scores of one detection, computed by the very device functions the search
+// loops call (hypothesis<ExactF32> / eval_pair<PackFast>), so tests can compare them with the oracle
+// hypothesis by hypothesis
+// ---------------------------------------------------------------------------------------------------
+__global__ void scores_exact_kernel(PollArgs<float> a, int32_t *votes, float *resid, int32_t *zneg) {
+    Detection<ExactF32> det;
+    load_detection<ExactF32, ExactF32>(det, a.boxes, a.dims, a.orient[0], a.pinv);
+    const float4 *pl = reinterpret_cast<const float4 *>(a.planes);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_planes; j += gridDim.x * blockDim.x) {
+        float X[4][3];
+        int V; float R; bool z;
+        hypothesis<ExactF32>(det, pl[j].x, pl[j].y, pl[j].z, pl[j].w, X, V, R, z);
+        votes[j] = V; resid[j] = R; zneg[j] = z ? 1 : 0;
+    }
+}
+
+template <bool kSix>
+__global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *resid, int32_t *zneg) {
+    DetConst D;
+    {
+        Detection<ExactF32> det;
+        load_detection<ExactF32, ExactF32>(det, a.boxes, a.dims, a.orient[0], a.pinv);
+        for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
+        for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
+        D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
+        D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
+    }
+    const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.pairs);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
+        const ulonglong2 v0 = pairs[2 * p], v1 = pairs[2 * p + 1];
+        PairResult h;
+        eval_pair<kSix>(PackFast(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+        const f2 R = resid_sum(h);
+        const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+        const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+        votes[2 * p] = V0; resid[2 * p] = lo(R); zneg[2 * p] = lo(h.zc) < 0.0f ? 1 : 0;
+        if (2 * p + 1 < a.n_planes) {
+            votes[2 * p + 1] = V1; resid[2 * p + 1] = hi(R); zneg[2 * p + 1] = hi(h.zc) < 0.0f ? 1 : 0;
+        }
+    }
+}
+
+int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const int32_t *d_orient, int which,
+                  int32_t *votes, float *resid, int32_t *zneg, cudaStream_t s) {
+    const int threads = 128, blocks = 64;
+    if (which == 0) {
+        PollArgs<float> a = {};
+        a.boxes = d_det; a.dims = d_det + 12; a.pinv = d_det + 15; a.orient = d_orient;
+        a.planes = h->d_planes32; a.n_planes = h->n_planes;
+        scores_exact_kernel<<<blocks, threads, 0, s>>>(a, votes, resid, zneg);
+    } else {
+        PollArgs2<float> b = {};
+        b.boxes = d_det; b.dims = d_det + 12; b.pinv = d_det + 15; b.orient = d_orient;
+        b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
+        b.n_pairs_padded = h->n_pairs_padded;
+        if (which == 1) scores_fast_kernel<false><<<blocks, threads, 0, s>>>(b, votes, resid, zneg);
+        else scores_fast_kernel<true><<<blocks, threads, 0, s>>>(b, votes, resid, zneg);
+    }
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "scores kernel launch: %s", cudaGetErrorString(e));
     return GPP_OK;
 }
 

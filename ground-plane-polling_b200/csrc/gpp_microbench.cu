@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, flo
                     if ((i & 3) == 0) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(alu[(i >> 2) & 3]));
                 }
             }
-            if (KIND == 1 || KIND == 7) { // packed f32x2: 8 register pairs
+            if (KIND == 1 || KIND == 7 || KIND >= 9) { // packed f32x2: 8 register pairs
                 unsigned long long *p = reinterpret_cast<unsigned long long *>(acc);
                 unsigned long long pa, pb;
                 asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
@@ -54,9 +54,16 @@ __global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, flo
                     for (int i = 0; i < kChains / 2; ++i) {
                         if (KIND == 1) {
                             asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb));
-                        } else {
+                        } else if (KIND == 7) {   // FMUL2 only (ptxas would fuse a dependent mul+add pair)
                             asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa));
+                        } else if (KIND == 9) {   // FADD2 only
                             asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+                        } else if (KIND == 10) {  // independent FMUL2 and FADD2 streams, 1:1
+                            if (i & 1) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa));
+                            else       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+                        } else {                  // KIND 11: FFMA2 and FADD2 streams, 1:1
+                            if (i & 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb));
+                            else       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
                         }
                     }
             }
@@ -128,7 +135,10 @@ extern "C" int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float 
         case 4: rc = gpp::run_kind<4>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
         case 5: rc = gpp::run_kind<5>(h, per, ops_per_s, ms, ops_per_clk_sm); break;           // FFMA count only
         case 6: rc = gpp::run_kind<6>(h, per, ops_per_s, ms, ops_per_clk_sm); break;
-        case 7: rc = gpp::run_kind<7>(h, per * 4, ops_per_s, ms, ops_per_clk_sm); break;       // (mul+add) x 2 lanes x 2 reps
+        case 7: rc = gpp::run_kind<7>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;       // 2 x 8 pairs x 2 lanes
+        case 9: rc = gpp::run_kind<9>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
+        case 10: rc = gpp::run_kind<10>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
+        case 11: rc = gpp::run_kind<11>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;     // packed instr x 2 lanes
         case 8: rc = gpp::run_kind<8>(h, per, ops_per_s, ms, ops_per_clk_sm); break;           // FFMA count only
         default: rc = gpp::set_error(GPP_EINVAL, "gpp_microbench: unknown kind %d", kind);
     }

@@ -102,7 +102,8 @@ struct PackFast {
 struct DetConst {
     float dl[3], dm[3], dr[3], dt[3];
     float td[6];
-    float T;           // |d_t|^2 (fast formulation only)
+    float T;           // |d_t|^2  (fast formulation only)
+    float G;           // d_t . d_m (fast formulation only)
 };
 
 struct PairResult {
@@ -117,8 +118,10 @@ __device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, flo
 }
 
 // ---- EXACT: the canonical op order of oracle/fit_road_planes_ref.py, two planes at a time
+template <bool kSix>
 __device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
-                                          PairResult &out, f2 X[4][3]) {
+                                          PairResult &out) {
+    f2 X[4][3];
     const float *rays[3] = {D.dl, D.dm, D.dr};
     const f2 nd = neg2(d4);
 #pragma unroll
@@ -155,50 +158,73 @@ __device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f
     }
 }
 
-// ---- FAST: FMA contraction, MUFU reciprocal / square root, and algebra that is exact in real arithmetic:
-//   perp = d_t x (n x d_t) = n |d_t|^2 - d_t (n.d_t);  perp.n = |d_t|^2 - (n.d_t)^2 for a unit normal;
-//   X_l - X_t = (X_l - X_m) + q n,  X_r - X_t = (X_r - X_m) + q n,  |X_m - X_t| = |q|.
-__device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
-                                          PairResult &out, f2 X[4][3]) {
-    const float *rays[3] = {D.dl, D.dm, D.dr};
+// ---- FAST: FMA contraction, MUFU reciprocal / square root, and algebra that is exact in real arithmetic.
+// All packed FP32 instructions (FFMA2 / FMUL2 / FADD2) retire 128 results/clk/SM like their scalar forms
+// (measured), so what counts is the number of FMA-pipe results per hypothesis.  With a unit normal n and
+// X_k = d_k |d / t_k| (t_k = n.d_k) every intersection point lies on the (+-) plane, n.X_k = |d| sign(t_k),
+// which removes most of calc_X_t:
+//   perp = d_t x (n x d_t) = n T - d_t u            (T = |d_t|^2, u = n.d_t)
+//   perp.n   = T - u^2
+//   perp.X_m = T |d| sign(t_m) - u s_m G            (G = d_t.d_m)
+//   X_t = X_m - q n,  |X_m - X_t| = |q|
+//   |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
+// 60 FMA-pipe results, 9 MUFU and ~11 ALU-pipe instructions per hypothesis (the direct formulation: 92 / 10).
+template <bool kMergedRcp>
+__device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
+    const f2 t0 = dot3p(n0, n1, n2, D.dl[0], D.dl[1], D.dl[2], false);
+    const f2 t1 = dot3p(n0, n1, n2, D.dm[0], D.dm[1], D.dm[2], false);
+    const f2 t2 = dot3p(n0, n1, n2, D.dr[0], D.dr[1], D.dr[2], false);
+    const f2 u = dot3p(n0, n1, n2, D.dt[0], D.dt[1], D.dt[2], false);
+    const f2 den = fma2(neg2(u), u, bc(D.T));
     const f2 ad = abs2(d4);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        f2 t = dot3p(n0, n1, n2, rays[k][0], rays[k][1], rays[k][2], false);
-        f2 s = mul2(ad, PackFast::rcp(abs2(t)));
-        X[k][0] = mul2(bc(rays[k][0]), s);
-        X[k][1] = mul2(bc(rays[k][1]), s);
-        X[k][2] = mul2(bc(rays[k][2]), s);
+    f2 i0, i1;
+    if (kMergedRcp) {
+        // 1/t_l and 1/t_m from one MUFU.RCP (the MUFU unit, 16 results/clk/SM, is the other scarce pipe).  Only
+        // used once max-votes is known to be 6, where a degenerate (inf/NaN) hypothesis can neither win nor
+        // change max-votes.
+        const f2 inv = PackFast::rcp(mul2(t0, t1));
+        i0 = mul2(inv, t1);
+        i1 = mul2(inv, t0);
+    } else {
+        i0 = PackFast::rcp(t0);
+        i1 = PackFast::rcp(t1);
     }
+    const f2 s0 = mul2(ad, abs2(i0));
+    const f2 s1 = mul2(ad, abs2(i1));
+    const f2 s2 = mul2(ad, PackFast::rcp(abs2(t2)));
+    const f2 iden = PackFast::rcp(den);
+    // n.X_k = |d| sign(t_k): sign transfer on the ALU pipe
+    const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
+    const f2 cs1 = pk(copysignf(lo(ad), lo(t1)), copysignf(hi(ad), hi(t1)));
+    const f2 cs2 = pk(copysignf(lo(ad), lo(t2)), copysignf(hi(ad), hi(t2)));
     f2 a[3], b[3], c[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        a[i] = sub2(X[0][i], X[1][i]);          // X_l - X_m
-        b[i] = sub2(X[2][i], X[1][i]);          // X_r - X_m
-        c[i] = sub2(a[i], b[i]);                // X_l - X_r
+        const f2 nxm = neg2(mul2(bc(D.dm[i]), s1));      // -X_m
+        a[i] = fma2(bc(D.dl[i]), s0, nxm);               // X_l - X_m
+        b[i] = fma2(bc(D.dr[i]), s2, nxm);               // X_r - X_m
+        c[i] = sub2(a[i], b[i]);                         // X_l - X_r
     }
     out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
-    const float *dt = D.dt;
-    f2 u = dot3p(n0, n1, n2, dt[0], dt[1], dt[2], false);
-    f2 nu = neg2(u);
-    f2 p0 = fma2(bc(dt[0]), nu, mul2(n0, bc(D.T)));
-    f2 p1 = fma2(bc(dt[1]), nu, mul2(n1, bc(D.T)));
-    f2 p2 = fma2(bc(dt[2]), nu, mul2(n2, bc(D.T)));
-    f2 num = fma2(p2, X[1][2], fma2(p1, X[1][1], mul2(p0, X[1][0])));
-    f2 den = fma2(nu, u, bc(D.T));
-    f2 q = mul2(num, PackFast::rcp(den));
-    f2 e[3], f[3];
-    e[0] = fma2(q, n0, a[0]); e[1] = fma2(q, n1, a[1]); e[2] = fma2(q, n2, a[2]);     // X_l - X_t
-    f[0] = fma2(q, n0, b[0]); f[1] = fma2(q, n1, b[1]); f[2] = fma2(q, n2, b[2]);     // X_r - X_t
+    const f2 num = fma2(mul2(u, s1), bc(-D.G), mul2(cs1, bc(D.T)));
+    const f2 q = mul2(num, iden);
 #define GPP_SQN(v) fma2(v[2], v[2], fma2(v[1], v[1], mul2(v[0], v[0])))
-    out.r[0] = sub2(abs2(q), bc(D.td[0]));
-    out.r[1] = sub2(PackFast::sqrt(GPP_SQN(a)), bc(D.td[1]));
-    out.r[2] = sub2(PackFast::sqrt(GPP_SQN(b)), bc(D.td[2]));
-    out.r[3] = sub2(PackFast::sqrt(GPP_SQN(c)), bc(D.td[3]));
-    out.r[4] = sub2(PackFast::sqrt(GPP_SQN(e)), bc(D.td[4]));
-    out.r[5] = sub2(PackFast::sqrt(GPP_SQN(f)), bc(D.td[5]));
+    const f2 na = GPP_SQN(a), nb = GPP_SQN(b), nc = GPP_SQN(c);
 #undef GPP_SQN
-    (void)X;
+    const f2 an = sub2(cs0, cs1), bn = sub2(cs2, cs1);
+    const f2 ne = fma2(q, fma2(an, bc(2.0f), q), na);    // |X_l - X_t|^2
+    const f2 nf = fma2(q, fma2(bn, bc(2.0f), q), nb);    // |X_r - X_t|^2
+    out.r[0] = sub2(abs2(q), bc(D.td[0]));
+    out.r[1] = sub2(PackFast::sqrt(na), bc(D.td[1]));
+    out.r[2] = sub2(PackFast::sqrt(nb), bc(D.td[2]));
+    out.r[3] = sub2(PackFast::sqrt(nc), bc(D.td[3]));
+    out.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+    out.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+}
+template <bool kSix>
+__device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
+                                          PairResult &out) {
+    eval_pair_fast<kSix>(D, n0, n1, n2, d4, out);
 }
 
 // residual sum ((((|r0|+|r1|)+|r2|)+|r3|)+|r4|)+|r5| for both planes of the pair
@@ -305,6 +331,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
 #pragma unroll
             for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
             D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
+            D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
         }
         LaneState<float> st;                 // general mode (max votes not yet known to be 6)
         st.reset(FLT_MAX);
@@ -325,8 +352,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     const int p = (r << 5) + lane;
                     const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                     PairResult h;
-                    f2 X[4][3];
-                    eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                    eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
                     const f2 R = resid_sum(h);
                     const int j = 2 * (base_pair + p);
                     const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
@@ -350,8 +376,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                 const int p = (r << 5) + lane;
                 const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                 PairResult h;
-                f2 X[4][3];
-                eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                eval_pair<true>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
                 const f2 R = resid_sum(h);
                 const int j = 2 * (base_pair + p);
                 b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
@@ -394,8 +419,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                 const ulonglong2 v0 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p];
                 const ulonglong2 v1 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p + 1];
                 PairResult h;
-                f2 X[4][3];
-                eval_pair(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h, X);
+                eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
                 const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
                 const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
                 const bool mk0 = (2 * p < N) && ((V0 < Mw) || (lo(h.zc) < 0.0f));

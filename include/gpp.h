@@ -121,14 +121,23 @@ int64_t gpp_launch_count(const gpp_handle *h);
 /* FP32 CUDA-core pipe microbenchmarks on the handle's device (the roofline denominator of this path):
  * `kind` 0 = FFMA (3 register operands), 1 = packed FFMA2 (fma.rn.f32x2), 2 = FMUL+FADD uncontracted,
  * 3 = MUFU.RCP, 4 = MUFU.RSQ, 5 = FFMA with one ALU-pipe FMNMX per FFMA (FFMAs counted),
- * 6 = sqrt.approx, 7 = packed FMUL2+FADD2, 8 = FFMA with one MUFU.RCP per 4 FFMA (FFMAs counted).
+ * 6 = sqrt.approx, 7 = packed FMUL2, 8 = FFMA with one MUFU.RCP per 4 FFMA (FFMAs counted), 9 = packed FADD2,
+ * 10 = independent FMUL2 / FADD2 streams 1:1, 11 = independent FFMA2 / FADD2 streams 1:1 (packed kinds count
+ * two results per instruction).
  * Returns operations per second (an FMA counts as ONE operation; x2 for FLOP), the duration of the best
  * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
 
-/* Tuning hook (benchmarks only): reserved (ignored) and resident CTAs per
- * SM used to size the persistent grid (0 = occupancy maximum). */
-int gpp_debug_set_config(gpp_handle *h, int dets_per_warp, int ctas_per_sm);
+/* Tuning hook (benchmarks only): `variant` 2 / 3 / 4 selects the fp32 kernel compiled for that many resident
+ * CTAs per SM (register budget 128 / 80 / 64; 0 = built-in default), `ctas_per_sm` sizes the persistent grid
+ * (0 = occupancy maximum). */
+int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
+
+/* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same
+ * device functions the search loops call -- `which` 0 = EXACT arithmetic, 1 = FAST (general path), 2 = FAST
+ * (all-six-votes path, merged reciprocal).  votes / zneg: N int32, resid: N floats (host memory). */
+int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
+                     int which, int32_t *votes, float *resid, int32_t *zneg);
 
 #ifdef __cplusplus
 }

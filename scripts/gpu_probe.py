@@ -17,7 +17,7 @@ from gpp_b200.utils import synthetic  # noqa: E402
 out = {}
 poller = gpp_b200.get_poller(0)
 kinds = {0: 'ffma', 1: 'ffma2', 2: 'fmul+fadd', 3: 'mufu.rcp', 4: 'mufu.rsq', 5: 'ffma+alu', 6: 'sqrt.approx',
-         7: 'fmul2+fadd2', 8: 'ffma+rcp(4:1)'}
+         7: 'fmul2', 8: 'ffma+rcp(4:1)', 9: 'fadd2', 10: 'fmul2|fadd2', 11: 'ffma2|fadd2'}
 mb = {}
 for k, name in kinds.items():
     r = poller.microbench(k)
@@ -51,8 +51,8 @@ def timeit(B, D, tag, mode, dpw=0, cps=0, reps=3):
 runs = []
 for mode in ('exact', 'fast', 'f64'):
     for (B, tag) in ((64, '10k'), (512, '22k')):
-        for dpw in (0,):
-            for cps in (0, 1, 2, 3):
+        for dpw in ((2, 3, 4) if mode != 'f64' else (0,)):
+            for cps in (0,):
                 if mode == 'f64' and cps not in (0, 2):
                     continue
                 r = timeit(B if mode != 'f64' else B // 4, 100, tag, mode, dpw, cps)
