@@ -6,10 +6,10 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgpp.so')
+LIB_PATH = os.environ.get('GPP_LIB_PATH') or os.path.join(HERE, 'libgpp.so')   # override: kernel experiments only
 
-GPP_MODE_EXACT, GPP_MODE_FAST, GPP_MODE_F64 = 0, 1, 2
-MODES = {'exact': GPP_MODE_EXACT, 'fast': GPP_MODE_FAST, 'f64': GPP_MODE_F64}
+GPP_MODE_EXACT, GPP_MODE_FAST, GPP_MODE_F64, GPP_MODE_VERIFIED = 0, 1, 2, 3
+MODES = {'exact': GPP_MODE_EXACT, 'fast': GPP_MODE_FAST, 'f64': GPP_MODE_F64, 'verified': GPP_MODE_VERIFIED}
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -44,7 +44,8 @@ SIGNATURES = {
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),
     'gpp_debug_set_config': (c_int, [c_void_p, c_int, c_int]),
-    'gpp_debug_scores': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'gpp_debug_scores': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
 }
 
 _LIB = None

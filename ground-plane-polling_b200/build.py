@@ -43,13 +43,20 @@ def is_stale():
 
 def _compile(src):
     obj = os.path.join(OBJ, src.replace('.cu', '.o'))
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+    extra = os.environ.get('GPP_NVCC_EXTRA', '').split()          # experiments only, e.g. -DGPP_M6_UNROLL=2
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     return src, obj, p.returncode, p.stdout
 
 
-def build_libgpp(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link libgpp.so.  Returns the library path."""
+def build_libgpp(force=False, verbose=False, out=None):
+    """Compile every CUDA source for sm_100a and link libgpp.so.  Returns the library path.
+    ``out`` (experiments only) links to another file name, e.g. a variant built with GPP_NVCC_EXTRA."""
+    global LIB, OBJ
+    if out:
+        LIB = os.path.join(HERE, out)
+        OBJ = os.path.join(HERE, 'build', out.replace('.so', ''))
+        force = True
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -73,4 +80,5 @@ def build_libgpp(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build_libgpp(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    _out = sys.argv[sys.argv.index('--out') + 1] if '--out' in sys.argv else None
+    print(build_libgpp(force='--force' in sys.argv, verbose='-v' in sys.argv, out=_out))

@@ -258,7 +258,7 @@ int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, c
     int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                             "gpp_fit_device");
     if (rc) return rc;
-    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST)
+    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST && mode != GPP_MODE_VERIFIED)
         return set_error(GPP_EINVAL, "gpp_fit_device: mode %d (use gpp_fit_device_f64 for the FP64 mode)", mode);
     if ((long long)B * D == 0) return GPP_OK;
     DeviceGuard guard(h->device);
@@ -401,7 +401,7 @@ int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, con
     int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                             "gpp_fit_host");
     if (rc) return rc;
-    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST)
+    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST && mode != GPP_MODE_VERIFIED)
         return set_error(GPP_EINVAL, "gpp_fit_host: mode %d (use gpp_fit_host_f64 for the FP64 mode)", mode);
     return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                                 best_index, mode);
@@ -440,7 +440,7 @@ int gpp_last_kernel_ms(gpp_handle *h, float *ms) {
 int64_t gpp_launch_count(const gpp_handle *h) { return h ? h->launches : 0; }
 
 int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
-                     int which, int32_t *votes, float *resid, int32_t *zneg) {
+                     int which, int32_t *votes, float *resid, int32_t *zneg, float *margin) {
     if (!h || !box12 || !dims3 || !pinv12 || !votes || !resid || !zneg || h->n_planes <= 0 || which < 0 || which > 2)
         return set_error(GPP_EINVAL, "gpp_debug_scores: bad argument");
     DeviceGuard guard(h->device);
@@ -452,7 +452,7 @@ int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int 
     float *d_det = nullptr, *d_res = nullptr;
     int32_t *d_int = nullptr;
     cudaError_t e = cudaMalloc(&d_det, sizeof(host_det));
-    if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(float) * 2 * (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&d_int, sizeof(int32_t) * (2 * (size_t)n + 1));
     int rc = GPP_OK;
     if (e == cudaSuccess) {
@@ -460,11 +460,16 @@ int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int 
         int32_t o = orientation;
         e = cudaMemcpyAsync(d_det, host_det, sizeof(host_det), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_int + 2 * (size_t)n, &o, sizeof(o), cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) rc = gpp::launch_scores(h, d_det, d_int + 2 * (size_t)n, which, d_int, d_res, d_int + n, s);
+        if (e == cudaSuccess && margin) e = cudaMemsetAsync(d_res + n, 0, sizeof(float) * n, s);
+        if (e == cudaSuccess)
+            rc = gpp::launch_scores(h, d_det, d_int + 2 * (size_t)n, which, d_int, d_res, d_int + n,
+                                    (margin && which > 0) ? d_res + n : nullptr, s);
         if (e == cudaSuccess && rc == GPP_OK) {
             e = cudaMemcpyAsync(votes, d_int, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaMemcpyAsync(zneg, d_int + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaMemcpyAsync(resid, d_res, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && margin)
+                e = cudaMemcpyAsync(margin, d_res + n, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         }
     }

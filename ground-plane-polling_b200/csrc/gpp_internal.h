@@ -53,6 +53,7 @@ struct gpp_handle {
     int force_variant = 0, force_ctas_per_sm = 0;
     int occ[3] = {0, 0, 0};                      // resident CTAs per SM: exact dpw 1, exact dpw 2, fp64
     int occ2[3] = {0, 0, 0};                     // fast kernel: [register-budget variant]
+    int occ3[2] = {0, 0};                        // verified kernel: [register-budget variant]
 };
 
 namespace gpp {
@@ -61,7 +62,7 @@ int configure_kernels(gpp_handle *h);
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s);
 int build_pairs(gpp_handle *h, cudaStream_t s);
 int launch_scores(gpp_handle *h, const float *d_det, const int32_t *d_orient, int which, int32_t *votes,
-                  float *resid, int32_t *zneg, cudaStream_t s);
+                  float *resid, int32_t *zneg, float *margin, cudaStream_t s);
 int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a, cudaStream_t s);
 inline int launch_poll(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
     return launch_poll_f32(h, a, mode, s);

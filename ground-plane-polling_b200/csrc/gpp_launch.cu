@@ -6,13 +6,22 @@
 #ifndef GPP_DEFAULT_VARIANT_FAST
 #define GPP_DEFAULT_VARIANT_FAST 1
 #endif
+#ifndef GPP_DEFAULT_VARIANT_VERIFIED
+#define GPP_DEFAULT_VARIANT_VERIFIED 1
+#endif
 
 namespace gpp {
 
 // CTA shape: 8 warps, 1024-plane tiles (32 KB fp32 pairs / 32 KB fp64), 3-stage TMA ring.
 constexpr int kWarps = 8;
-constexpr int kTile32 = 1024, kTile64 = 512;
-constexpr int kStages = 3;
+#ifndef GPP_TILE
+#define GPP_TILE 1024
+#endif
+#ifndef GPP_STAGES
+#define GPP_STAGES 3
+#endif
+constexpr int kTile32 = GPP_TILE, kTile64 = 512;
+constexpr int kStages = GPP_STAGES;
 
 // pair-interleaved, padded copy of the normalised fp32 database: pair p = planes (2p, 2p+1) stored as
 // {a0,a1,b0,b1,c0,c1,d0,d1}; planes past N-1 are copies of plane N-1 (same score, higher index: they can
@@ -74,6 +83,12 @@ static Poll2Fn fast_variant(int v) {
         default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 4>;
     }
 }
+static Poll2Fn verified_variant(int v) {
+    switch (v) {
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2, true>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, true>;
+    }
+}
 
 int configure_kernels(gpp_handle *h) {
     int rc;
@@ -81,21 +96,29 @@ int configure_kernels(gpp_handle *h) {
     if ((rc = configure_kernel(GPP_K_EXACT2, kSmem1, &h->occ[1]))) return rc;
     for (int v = 0; v < 3; ++v)
         if ((rc = configure_kernel(fast_variant(v), kSmem2, &h->occ2[v]))) return rc;
+    for (int v = 0; v < 2; ++v)
+        if ((rc = configure_kernel(verified_variant(v), kSmem2, &h->occ3[v]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64, kSmem64, &h->occ[2]))) return rc;
     return GPP_OK;
 }
 
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
-    if (mode == GPP_MODE_FAST) {
+    if (mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) {
         PollArgs2<float> b;
         b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
         b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
         b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
         const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
-        int v = GPP_DEFAULT_VARIANT_FAST;
-        if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
-        fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
+        if (mode == GPP_MODE_VERIFIED) {
+            int v = GPP_DEFAULT_VARIANT_VERIFIED;
+            if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
+            verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
+        } else {
+            int v = GPP_DEFAULT_VARIANT_FAST;
+            if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
+            fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
+        }
     } else {
         // two detections per warp once every SM has several groups to chew on
         const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
@@ -132,7 +155,7 @@ __global__ void scores_exact_kernel(PollArgs<float> a, int32_t *votes, float *re
 }
 
 template <bool kSix>
-__global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *resid, int32_t *zneg) {
+__global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *resid, int32_t *zneg, float *margin) {
     DetConst D;
     {
         Detection<ExactF32> det;
@@ -146,19 +169,21 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
         const ulonglong2 v0 = pairs[2 * p], v1 = pairs[2 * p + 1];
         PairResult h;
-        eval_pair<kSix>(PackFast(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+        eval_pair_fast<kSix, true>(D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
         const f2 R = resid_sum(h);
         const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
         const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
         votes[2 * p] = V0; resid[2 * p] = lo(R); zneg[2 * p] = lo(h.zc) < 0.0f ? 1 : 0;
+        if (margin) margin[2 * p] = lo(h.m);
         if (2 * p + 1 < a.n_planes) {
             votes[2 * p + 1] = V1; resid[2 * p + 1] = hi(R); zneg[2 * p + 1] = hi(h.zc) < 0.0f ? 1 : 0;
+            if (margin) margin[2 * p + 1] = hi(h.m);
         }
     }
 }
 
 int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const int32_t *d_orient, int which,
-                  int32_t *votes, float *resid, int32_t *zneg, cudaStream_t s) {
+                  int32_t *votes, float *resid, int32_t *zneg, float *margin, cudaStream_t s) {
     const int threads = 128, blocks = 64;
     if (which == 0) {
         PollArgs<float> a = {};
@@ -170,8 +195,8 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
         b.boxes = d_det; b.dims = d_det + 12; b.pinv = d_det + 15; b.orient = d_orient;
         b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
         b.n_pairs_padded = h->n_pairs_padded;
-        if (which == 1) scores_fast_kernel<false><<<blocks, threads, 0, s>>>(b, votes, resid, zneg);
-        else scores_fast_kernel<true><<<blocks, threads, 0, s>>>(b, votes, resid, zneg);
+        if (which == 1) scores_fast_kernel<false><<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
+        else scores_fast_kernel<true><<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
     }
     h->launches += 1;
     cudaError_t e = cudaGetLastError();

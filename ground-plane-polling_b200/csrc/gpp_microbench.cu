@@ -45,9 +45,16 @@ __global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, flo
             }
             if (KIND == 1 || KIND == 7 || KIND >= 9) { // packed f32x2: 8 register pairs
                 unsigned long long *p = reinterpret_cast<unsigned long long *>(acc);
-                unsigned long long pa, pb;
+                unsigned long long pa, pb, qv[8], qb[8];
                 asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
                 asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+                if (KIND >= 12) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(qv[i]) : "f"(alu[i & 3] + float(i)), "f"(alu[(i + 1) & 3] - float(i)));
+                        asm volatile("mov.b64 %0, {%1, %1};" : "=l"(qb[i]) : "f"(alu[(i + 2) & 3] * float(i + 1)));
+                    }
+                }
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)
 #pragma unroll
@@ -61,9 +68,13 @@ __global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, flo
                         } else if (KIND == 10) {  // independent FMUL2 and FADD2 streams, 1:1
                             if (i & 1) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa));
                             else       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
-                        } else {                  // KIND 11: FFMA2 and FADD2 streams, 1:1
+                        } else if (KIND == 11) {  // FFMA2 and FADD2 streams, 1:1
                             if (i & 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb));
                             else       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+                        } else if (KIND == 12) {  // FFMA2, three distinct 64-bit register operands per instruction
+                            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(qv[i]), "l"(qv[(i + 3) & 7]));
+                        } else {                  // KIND 13: FFMA2 acc = acc * bcast(32-bit reg) + other acc-sized reg
+                            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(qb[i]), "l"(qv[(i + 5) & 7]));
                         }
                     }
             }
@@ -139,6 +150,8 @@ extern "C" int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float 
         case 9: rc = gpp::run_kind<9>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
         case 10: rc = gpp::run_kind<10>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
         case 11: rc = gpp::run_kind<11>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;     // packed instr x 2 lanes
+        case 12: rc = gpp::run_kind<12>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
+        case 13: rc = gpp::run_kind<13>(h, per * 2, ops_per_s, ms, ops_per_clk_sm); break;
         case 8: rc = gpp::run_kind<8>(h, per, ops_per_s, ms, ops_per_clk_sm); break;           // FFMA count only
         default: rc = gpp::set_error(GPP_EINVAL, "gpp_microbench: unknown kind %d", kind);
     }

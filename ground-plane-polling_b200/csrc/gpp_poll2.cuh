@@ -14,6 +14,12 @@
 #pragma once
 #include "gpp_poll.cuh"
 
+#ifndef GPP_M6_UNROLL
+#define GPP_M6_UNROLL 1
+#endif
+#define GPP_PRAGMA_(x) _Pragma(#x)
+#define GPP_UNROLL(n) GPP_PRAGMA_(unroll n)
+
 namespace gpp {
 
 typedef unsigned long long u64;
@@ -109,7 +115,18 @@ struct DetConst {
 struct PairResult {
     f2 r[6];           // signed residuals dist_k - target_k (abs is applied by the consumers)
     f2 zc;             // z_dir_check
+    f2 m;              // VERIFIED mode: bound on |fast - exact| of the residual sum (see eval_pair_fast)
 };
+
+// Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
+// score mainly through the rounding of t_k = n.d_k (absolute ~u) divided by |t_k|: a point at distance
+// |X_k| = |d_k| |d| / |t_k| moves by ~ u |X_k| / |t_k|, i.e. ~ u |d| i_max^2 with i_k = 1/|t_k| (quadratic in
+// depth), and X_t additionally by ~1/(perp.n).  kMarginK is that first-order scale times a safety factor; the
+// VERIFIED mode is validated against the EXACT mode on full benchmark batches (tests/test_verified_gpu.py).
+#ifndef GPP_MARGIN_K
+#define GPP_MARGIN_K 64.0f
+#endif
+constexpr float kMarginScale = GPP_MARGIN_K * 5.9604645e-8f;   // K * 2^-24
 
 __device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, float b2, bool exact) {
     // (a0*b0 + a1*b1) + a2*b2, exact: three multiplies and two adds; fast: multiply + two FMAs
@@ -169,7 +186,7 @@ __device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f
 //   X_t = X_m - q n,  |X_m - X_t| = |q|
 //   |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
 // 60 FMA-pipe results, 9 MUFU and ~11 ALU-pipe instructions per hypothesis (the direct formulation: 92 / 10).
-template <bool kMergedRcp>
+template <bool kMergedRcp, bool kMargin>
 __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
     const f2 t0 = dot3p(n0, n1, n2, D.dl[0], D.dl[1], D.dl[2], false);
     const f2 t1 = dot3p(n0, n1, n2, D.dm[0], D.dm[1], D.dm[2], false);
@@ -191,8 +208,14 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
     }
     const f2 s0 = mul2(ad, abs2(i0));
     const f2 s1 = mul2(ad, abs2(i1));
-    const f2 s2 = mul2(ad, PackFast::rcp(abs2(t2)));
+    const f2 i2 = PackFast::rcp(abs2(t2));
+    const f2 s2 = mul2(ad, i2);
     const f2 iden = PackFast::rcp(den);
+    if (kMargin) {
+        const f2 imax = pk(max3f(fabsf(lo(i0)), fabsf(lo(i1)), lo(i2)), max3f(fabsf(hi(i0)), fabsf(hi(i1)), hi(i2)));
+        const f2 w = mul2(mul2(imax, imax), ad);                         // |d| / t_min^2
+        out.m = mul2(w, fma2(abs2(iden), bc(kMarginScale * D.T), bc(kMarginScale)));   // K u w (1 + T/|perp.n|)
+    }
     // n.X_k = |d| sign(t_k): sign transfer on the ALU pipe
     const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
     const f2 cs1 = pk(copysignf(lo(ad), lo(t1)), copysignf(hi(ad), hi(t1)));
@@ -224,7 +247,7 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
 template <bool kSix>
 __device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
                                           PairResult &out) {
-    eval_pair_fast<kSix>(D, n0, n1, n2, d4, out);
+    eval_pair_fast<kSix, false>(D, n0, n1, n2, d4, out);
 }
 
 // residual sum ((((|r0|+|r1|)+|r2|)+|r3|)+|r4|)+|r5| for both planes of the pair
@@ -273,7 +296,17 @@ struct PollArgs2 {
 };
 
 // kTile planes per smem tile (multiple of 64), one detection per warp.
-template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks>
+// exact scalar evaluation of one plane of a pair (VERIFIED mode: general path, re-evaluation, epilogue)
+__device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n0, float n1, float n2, float d4,
+                                          int &V, float &R, bool &zneg) {
+    float X[4][3];
+    hypothesis<ExactF32>(de, n0, n1, n2, d4, X, V, R, zneg);
+}
+
+// kVerified: FAST arithmetic is only a filter -- every hypothesis that could be the arg-min within the error
+// margin is re-evaluated in the EXACT arithmetic and all selection state is kept in exact values, so the
+// result equals the EXACT mode's (see the header comment of the verified path below).
+template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, bool kVerified = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
     constexpr int kTilePairs = kTile / 2;
     constexpr uint32_t kPairBytes = 32;
@@ -322,22 +355,21 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         const long long m = g * kWarps + warp;
         const long long mm = m < args.n_det ? m : args.n_det - 1;
         DetConst D;
-        {
-            Detection<ExactF32> det;
-            load_detection<ExactF32, ExactF32>(det, args.boxes + 12 * mm, args.dims + 3 * mm,
-                                               __ldg(args.orient + mm), args.pinv + 12 * (mm / args.dets_per_image));
+        Detection<ExactF32> det;             // same registers as D (the copies below are free)
+        load_detection<ExactF32, ExactF32>(det, args.boxes + 12 * mm, args.dims + 3 * mm,
+                                           __ldg(args.orient + mm), args.pinv + 12 * (mm / args.dets_per_image));
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
+        for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
-            D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
-            D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
-        }
+        for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
+        D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
+        D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
         LaneState<float> st;                 // general mode (max votes not yet known to be 6)
         st.reset(FLT_MAX);
         LaneBest b6;                         // M == 6 mode
         b6.bestR = FLT_MAX; b6.bestIdx = 0;
         bool m6 = false;
+        float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
 
         for (int t = 0; t < n_tiles; ++t, ++it) {
             const int s = int(it % kStages);
@@ -351,15 +383,24 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                 for (; r < rows; ++r) {
                     const int p = (r << 5) + lane;
                     const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
-                    PairResult h;
-                    eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
-                    const f2 R = resid_sum(h);
                     const int j = 2 * (base_pair + p);
-                    const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
-                    const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-                    st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
-                    st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
-                    if ((r & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                    if (kVerified) {
+                        const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
+                        int V; float R; bool z;
+                        exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V, R, z);
+                        st.update(V, R, z, j, FLT_MAX);
+                        exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V, R, z);
+                        st.update(V, R, z, j + 1, FLT_MAX);
+                    } else {
+                        PairResult h;
+                        eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                        const f2 R = resid_sum(h);
+                        const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                        const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                        st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
+                        st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
+                    }
+                    if ((kVerified || (r & 3) == 3) && __reduce_max_sync(0xffffffffu, st.M) == 6) {
                         m6 = true;                               // warp-uniform decision
                         ++r;
                         break;
@@ -369,20 +410,55 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     // candidates found under a lower running max are masked from now on
                     b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
                     b6.bestIdx = st.bestIdx;
+                    if (kVerified) wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
                 }
             }
-#pragma unroll 1
+GPP_UNROLL(GPP_M6_UNROLL)
             for (; r < rows; ++r) {
                 const int p = (r << 5) + lane;
                 const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                 PairResult h;
-                eval_pair<true>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
-                const f2 R = resid_sum(h);
                 const int j = 2 * (base_pair + p);
-                b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                           lo(h.zc), lo(R), j);
-                b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
-                           hi(h.zc), hi(R), j + 1);
+                if (kVerified) {
+                    // ---- filter: a plane can only matter if, within its error margin, it has all six votes,
+                    // passes the z-check and scores no worse than the warp's best exact residual so far
+                    eval_pair_fast<true, true>(D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    const f2 R = resid_sum(h);
+                    const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                                     rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+                    const f2 rlo = sub2(rm, h.m);                       // lower bounds (margin subtracted)
+                    const f2 Rlo = sub2(R, h.m);
+                    const f2 zhi = fma2(h.m, bc(16.0f), h.zc);          // upper bound of z_dir_check
+                    // comparisons written so that NaN (degenerate fast arithmetic) always triggers
+                    const bool trig0 = !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
+                    const bool trig1 = !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+                    if (__any_sync(0xffffffffu, trig0 || trig1)) {
+                        const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
+                        if (trig0) {
+                            int V; float Rx; bool z;
+                            exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V, Rx, z);
+                            const bool better = (V == 6) && !z && (Rx < b6.bestR);
+                            b6.bestR = better ? Rx : b6.bestR;
+                            b6.bestIdx = better ? j : b6.bestIdx;
+                        }
+                        if (trig1) {
+                            int V; float Rx; bool z;
+                            exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V, Rx, z);
+                            const bool better = (V == 6) && !z && (Rx < b6.bestR);
+                            b6.bestR = better ? Rx : b6.bestR;
+                            b6.bestIdx = better ? j + 1 : b6.bestIdx;
+                        }
+                        __syncwarp();
+                        wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+                    }
+                } else {
+                    eval_pair<true>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    const f2 R = resid_sum(h);
+                    b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                               lo(h.zc), lo(R), j);
+                    b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
+                               hi(h.zc), hi(R), j + 1);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -418,12 +494,23 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                 const int p = p0 + lane;                         // pair index; the padded DB covers it
                 const ulonglong2 v0 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p];
                 const ulonglong2 v1 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p + 1];
-                PairResult h;
-                eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
-                const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
-                const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-                const bool mk0 = (2 * p < N) && ((V0 < Mw) || (lo(h.zc) < 0.0f));
-                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || (hi(h.zc) < 0.0f));
+                int V0, V1;
+                bool z0, z1;
+                if (kVerified) {
+                    const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
+                    float Rx;
+                    exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V0, Rx, z0);
+                    exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V1, Rx, z1);
+                } else {
+                    PairResult h;
+                    eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                    V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                    z0 = lo(h.zc) < 0.0f;
+                    z1 = hi(h.zc) < 0.0f;
+                }
+                const bool mk0 = (2 * p < N) && ((V0 < Mw) || z0);
+                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || z1);
                 const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
                 if (b0 | b1) {
                     const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
@@ -442,14 +529,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         }
         if (m < args.n_det && lane == 0) {
             const float4 pl = args.planes[idx];
-            Detection<ExactF32> de;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { de.dl[i] = D.dl[i]; de.dm[i] = D.dm[i]; de.dr[i] = D.dr[i]; de.dt[i] = D.dt[i]; }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) de.td[i] = D.td[i];
             float X[4][3];
             int V; float R; bool zneg;
-            hypothesis<ExactF32>(de, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            hypothesis<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
             const float rr = sentinel ? 100.0f : R;
             float *kp = args.keypoints + 12 * m;
 #pragma unroll

@@ -199,15 +199,19 @@ class PlanePoller(object):
                                             ctypes.byref(opc)), 'gpp_microbench')
         return dict(ops_per_s=ops.value, ms=ms.value, ops_per_clk_sm=opc.value)
 
-    def debug_scores(self, box12, dims3, orientation, pinv12, which=0):
-        """Test hook: (votes, residual sum, z_dir_check < 0) of one detection against every resident plane,
-        from the device functions of the search loop (which: 0 exact, 1 fast general, 2 fast all-six path)."""
+    def debug_scores(self, box12, dims3, orientation, pinv12, which=0, with_margin=False):
+        """Test hook: (votes, residual sum, z_dir_check < 0 [, margin]) of one detection against every
+        resident plane, from the device functions of the search loop (which: 0 exact, 1 fast general, 2 fast
+        all-six path); margin = the VERIFIED mode's bound on |fast - exact| of the residual sum."""
         n = self.num_planes
         votes, zneg, resid = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32)
+        margin = np.zeros(n, np.float32) if with_margin else None
         rc = self._lib.gpp_debug_scores(self._h, _lib.ptr(_f32(box12).reshape(12)), _lib.ptr(_f32(dims3).reshape(3)),
                                         int(orientation), _lib.ptr(_f32(pinv12).reshape(12)), int(which),
-                                        _lib.ptr(votes), _lib.ptr(resid), _lib.ptr(zneg))
+                                        _lib.ptr(votes), _lib.ptr(resid), _lib.ptr(zneg), _lib.ptr(margin))
         _lib.check(rc, 'gpp_debug_scores')
+        if with_margin:
+            return votes, resid, zneg.astype(bool), margin
         return votes, resid, zneg.astype(bool)
 
     def debug_set_config(self, variant=0, ctas_per_sm=0):

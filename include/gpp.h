@@ -43,8 +43,11 @@ enum {
  *            key-points / residual are then recomputed with the EXACT arithmetic.  May pick a different
  *            plane only when two planes score within float rounding noise of each other.
  *   F64    : the same search in IEEE fp64 (verify mode for near-ties); only through gpp_fit_*_f64.
+ *   VERIFIED: the FAST arithmetic is used only as a filter; every plane that, within a conservative bound on
+ *            the fast-vs-exact deviation, could be the arg-min is re-evaluated in the EXACT arithmetic, and
+ *            all selection state is kept in exact values -> same results as EXACT at close to FAST speed.
  */
-enum { GPP_MODE_EXACT = 0, GPP_MODE_FAST = 1, GPP_MODE_F64 = 2 };
+enum { GPP_MODE_EXACT = 0, GPP_MODE_FAST = 1, GPP_MODE_F64 = 2, GPP_MODE_VERIFIED = 3 };
 
 typedef struct gpp_handle gpp_handle;
 
@@ -122,8 +125,9 @@ int64_t gpp_launch_count(const gpp_handle *h);
  * `kind` 0 = FFMA (3 register operands), 1 = packed FFMA2 (fma.rn.f32x2), 2 = FMUL+FADD uncontracted,
  * 3 = MUFU.RCP, 4 = MUFU.RSQ, 5 = FFMA with one ALU-pipe FMNMX per FFMA (FFMAs counted),
  * 6 = sqrt.approx, 7 = packed FMUL2, 8 = FFMA with one MUFU.RCP per 4 FFMA (FFMAs counted), 9 = packed FADD2,
- * 10 = independent FMUL2 / FADD2 streams 1:1, 11 = independent FFMA2 / FADD2 streams 1:1 (packed kinds count
- * two results per instruction).
+ * 10 = independent FMUL2 / FADD2 streams 1:1, 11 = independent FFMA2 / FADD2 streams 1:1, 12 = FFMA2 with three
+ * distinct 64-bit register operands, 13 = FFMA2 with a broadcast 32-bit operand (packed kinds count two
+ * results per instruction).
  * Returns operations per second (an FMA counts as ONE operation; x2 for FLOP), the duration of the best
  * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
@@ -135,9 +139,10 @@ int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
 
 /* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same
  * device functions the search loops call -- `which` 0 = EXACT arithmetic, 1 = FAST (general path), 2 = FAST
- * (all-six-votes path, merged reciprocal).  votes / zneg: N int32, resid: N floats (host memory). */
+ * (all-six-votes path, merged reciprocal).  votes / zneg: N int32, resid: N floats (host memory); margin: N
+ * floats or NULL -- the VERIFIED mode's bound on |fast - exact| of the residual sum (0 for which = 0). */
 int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
-                     int which, int32_t *votes, float *resid, int32_t *zneg);
+                     int which, int32_t *votes, float *resid, int32_t *zneg, float *margin);
 
 #ifdef __cplusplus
 }

