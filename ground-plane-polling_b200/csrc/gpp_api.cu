@@ -147,6 +147,11 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->d_planes32);
     cudaFree(h->d_planes64);
     cudaFree(h->d_pairs);
+    for (auto &w : h->work) {
+        cudaFree(w.list);
+        cudaFree(w.count);
+        if (w.done) cudaEventDestroy(w.done);
+    }
     for (int i = 0; i < gpp_handle::kStreams; ++i) {
         h->stage[i].release();
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -268,6 +273,7 @@ int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, c
     a.planes = h->d_planes32; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
     a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
     a.best = reinterpret_cast<long long *>(best_index);
+    a.det_list = nullptr; a.det_count = nullptr;
     GPP_CUDA(cudaEventRecord(h->ev_start, s));
     rc = gpp::launch_poll_f32(h, a, mode, s);
     if (rc) return rc;
@@ -291,6 +297,7 @@ int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimension
     a.planes = h->d_planes64; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
     a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
     a.best = reinterpret_cast<long long *>(best_index);
+    a.det_list = nullptr; a.det_count = nullptr;
     GPP_CUDA(cudaEventRecord(h->ev_start, s));
     rc = gpp::launch_poll_f64(h, a, s);
     if (rc) return rc;
@@ -377,6 +384,7 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         a.keyplanes = static_cast<T *>(st.keyplanes);
         a.residuals = static_cast<T *>(st.residuals);
         a.best = best ? st.best : nullptr;
+        a.det_list = nullptr; a.det_count = nullptr;
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].first, s));
         int rc = gpp::launch_poll(h, a, mode, s);
         if (rc) return rc;

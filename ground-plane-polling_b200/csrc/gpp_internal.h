@@ -36,6 +36,18 @@ struct gpp_handle {
     float *d_raw = nullptr;
     float4 *d_planes32 = nullptr;
     double4 *d_planes64 = nullptr;
+    // VERIFIED mode: detections deferred to the EXACT second pass.  A small ring of work lists, each guarded
+    // by an event, so that launches in flight on different streams never share one.
+    struct WorkSlot {
+        long long *list = nullptr;
+        unsigned int *count = nullptr;
+        long long cap = 0;
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    static constexpr int kWorkSlots = 4;
+    WorkSlot work[kWorkSlots];
+    unsigned next_work = 0;
     unsigned long long *d_pairs = nullptr;   // pair-interleaved fp32 copy, padded to 64 planes (gpp_poll2.cuh)
     int n_pairs_padded = 0;
     int n_planes = 0, cap_planes = 0;

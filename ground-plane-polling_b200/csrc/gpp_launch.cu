@@ -63,7 +63,8 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
     return grid < 1 ? 1 : grid;
 }
 
-constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t);
+constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t) +
+                          sizeof(int) * kWarps * kVerifyQueue;
 constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t);
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
 
@@ -102,6 +103,25 @@ int configure_kernels(gpp_handle *h) {
     return GPP_OK;
 }
 
+static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_handle::WorkSlot **out) {
+    gpp_handle::WorkSlot &w = h->work[h->next_work++ % gpp_handle::kWorkSlots];
+    cudaError_t e = cudaSuccess;
+    if (!w.done) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
+    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, sizeof(unsigned int));
+    if (e == cudaSuccess && w.used) e = cudaStreamWaitEvent(s, w.done, 0);   // previous user of this slot
+    if (e == cudaSuccess && n_det > w.cap) {
+        // cudaMalloc/cudaFree are not stream-ordered: the previous user must be finished on the host side too
+        if (w.used) e = cudaEventSynchronize(w.done);
+        if (e == cudaSuccess) { cudaFree(w.list); w.list = nullptr; w.cap = 0; }
+        if (e == cudaSuccess) e = cudaMalloc(&w.list, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) w.cap = n_det;
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "work list setup: %s", cudaGetErrorString(e));
+    *out = &w;
+    return GPP_OK;
+}
+
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
     if (mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) {
         PollArgs2<float> b;
@@ -109,11 +129,23 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStrea
         b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
         b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
+        b.defer_list = nullptr; b.defer_count = nullptr;
         const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
             if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
+            gpp_handle::WorkSlot *w = nullptr;
+            int rc = reserve_worklist(h, a.n_det, s, &w);
+            if (rc) return rc;
+            b.defer_list = w->list; b.defer_count = w->count;
             verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
+            // second pass: the deferred detections in the scalar EXACT kernel (count read on the device)
+            PollArgs<float> c = a;
+            c.det_list = w->list; c.det_count = w->count;
+            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
+            h->launches += 1;
+            w->used = true;
+            cudaEventRecord(w->done, s);
         } else {
             int v = GPP_DEFAULT_VARIANT_FAST;
             if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
@@ -187,6 +219,7 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
     const int threads = 128, blocks = 64;
     if (which == 0) {
         PollArgs<float> a = {};
+        a.det_list = nullptr; a.det_count = nullptr;
         a.boxes = d_det; a.dims = d_det + 12; a.pinv = d_det + 15; a.orient = d_orient;
         a.planes = h->d_planes32; a.n_planes = h->n_planes;
         scores_exact_kernel<<<blocks, threads, 0, s>>>(a, votes, resid, zneg);

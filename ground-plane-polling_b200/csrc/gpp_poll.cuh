@@ -63,6 +63,9 @@ struct PollArgs {
     T *keyplanes;                // (n_det, 4)
     T *residuals;                // (n_det)
     long long *best;             // (n_det) or nullptr
+    // optional work list (VERIFIED mode, second pass): process det_list[0 .. *det_count) instead of 0 .. n_det
+    const long long *det_list;
+    const unsigned int *det_count;
 };
 
 // ------------------------------------------------------------------ per-lane streaming selection state
@@ -124,7 +127,8 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
     const int warp = threadIdx.x >> 5;
     const int N = args.n_planes;
     const int n_tiles = (N + kTile - 1) / kTile;
-    const long long n_groups = (args.n_det + kGroup - 1) / kGroup;
+    const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
+    const long long n_groups = (n_work + kGroup - 1) / kGroup;
     const long long my_groups = (n_groups > blockIdx.x) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total_tiles = my_groups * n_tiles;
     const T4 *gplanes = reinterpret_cast<const T4 *>(args.planes);
@@ -163,8 +167,9 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
 #pragma unroll
         for (int q = 0; q < kDpw; ++q) {
             long long m = g * kGroup + (long long)warp * kDpw + q;
-            det_id[q] = m;
-            const long long mm = m < args.n_det ? m : args.n_det - 1;     // tail warps redo the last one
+            long long mm = m < n_work ? m : n_work - 1;                   // tail warps redo the last one
+            if (args.det_list) mm = args.det_list[mm];
+            det_id[q] = m < n_work ? mm : -1;
             load_detection<P, typename ExactOf<P>::type>(det[q], args.boxes + 12 * mm, args.dims + 3 * mm, __ldg(args.orient + mm),
                                  args.pinv + 12 * (mm / args.dets_per_image));
             st[q].reset(highest);
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
                     idx = 0;                                      // nothing compares below `highest`
                 }
             }
-            if (det_id[q] < args.n_det && lane == 0) {
+            if (det_id[q] >= 0 && lane == 0) {
                 // recompute the winner in the exact arithmetic of this scalar type (fit_road_planes.py:122-137)
                 typedef typename ExactOf<P>::type E;
                 const T4 pl = gplanes[idx];

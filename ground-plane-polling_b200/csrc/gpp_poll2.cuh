@@ -293,6 +293,10 @@ struct PollArgs2 {
     long long n_det;
     T *keypoints, *keyplanes, *residuals;
     long long *best;
+    // VERIFIED mode: detections whose max-votes is not known to be 6 after the first tile are handed to a
+    // second pass (scalar EXACT kernel over this work list) instead of slowing their CTA down
+    long long *defer_list;
+    unsigned int *defer_count;
 };
 
 // kTile planes per smem tile (multiple of 64), one detection per warp.
@@ -301,6 +305,20 @@ __device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n
                                           int &V, float &R, bool &zneg) {
     float X[4][3];
     hypothesis<ExactF32>(de, n0, n1, n2, d4, X, V, R, zneg);
+}
+
+constexpr int kVerifyQueue = 96;
+
+// VERIFIED: exact re-evaluation of one queued plane; the lane keeps the lexicographic minimum (residual, index)
+__device__ __forceinline__ bool verify_one(const Detection<ExactF32> &de, const float4 *__restrict__ planes, int j,
+                                           LaneBest &b) {
+    const float4 pl = planes[j];
+    int V; float R; bool z;
+    exact_one(de, pl.x, pl.y, pl.z, pl.w, V, R, z);
+    const bool better = (V == 6) && !z && (R < b.bestR || (R == b.bestR && j < b.bestIdx));
+    b.bestR = better ? R : b.bestR;
+    b.bestIdx = better ? j : b.bestIdx;
+    return V == 6;                               // max-votes == 6 is established (z-check or not)
 }
 
 // kVerified: FAST arithmetic is only a filter -- every hypothesis that could be the arg-min within the error
@@ -314,6 +332,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     ulonglong2 *tiles = reinterpret_cast<ulonglong2 *>(smem_raw);             // 2 x ulonglong2 per pair
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(kPairBytes) * kStages * kTilePairs);
     uint64_t *empty_bar = full_bar + kStages;
+    // VERIFIED: per-warp queue of plane indices that survived the fast filter (at most 31 + 64 entries)
+    int *queue = reinterpret_cast<int *>(empty_bar + kStages) + (threadIdx.x >> 5) * kVerifyQueue;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -370,6 +390,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         b6.bestR = FLT_MAX; b6.bestIdx = 0;
         bool m6 = false;
         float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
+        int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
+        bool six_seen = false;               // VERIFIED: some plane has six EXACT votes (warp-uniform)
 
         for (int t = 0; t < n_tiles; ++t, ++it) {
             const int s = int(it % kStages);
@@ -378,20 +400,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
             const int rows = min(kTilePairs, NP - t * kTilePairs) >> 5;
             const int base_pair = t * kTilePairs;
             int r = 0;
-            if (!m6) {
+            if (!kVerified && !m6) {
 #pragma unroll 1
                 for (; r < rows; ++r) {
                     const int p = (r << 5) + lane;
                     const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                     const int j = 2 * (base_pair + p);
-                    if (kVerified) {
-                        const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
-                        int V; float R; bool z;
-                        exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V, R, z);
-                        st.update(V, R, z, j, FLT_MAX);
-                        exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V, R, z);
-                        st.update(V, R, z, j + 1, FLT_MAX);
-                    } else {
+                    {
                         PairResult h;
                         eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
                         const f2 R = resid_sum(h);
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                         st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
                         st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
                     }
-                    if ((kVerified || (r & 3) == 3) && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                    if ((r & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
                         m6 = true;                               // warp-uniform decision
                         ++r;
                         break;
@@ -410,7 +425,6 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     // candidates found under a lower running max are masked from now on
                     b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
                     b6.bestIdx = st.bestIdx;
-                    if (kVerified) wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
                 }
             }
 GPP_UNROLL(GPP_M6_UNROLL)
@@ -429,27 +443,29 @@ GPP_UNROLL(GPP_M6_UNROLL)
                     const f2 rlo = sub2(rm, h.m);                       // lower bounds (margin subtracted)
                     const f2 Rlo = sub2(R, h.m);
                     const f2 zhi = fma2(h.m, bc(16.0f), h.zc);          // upper bound of z_dir_check
-                    // comparisons written so that NaN (degenerate fast arithmetic) always triggers
-                    const bool trig0 = !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
-                    const bool trig1 = !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+                    // comparisons written so that NaN (degenerate fast arithmetic) always triggers; until an exact
+                    // six-vote plane is known (max-votes == 6 established) every possible six-vote plane survives
+                    const bool trig0 = !(lo(rlo) > 0.7f) && (!six_seen || (!(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest)));
+                    const bool trig1 = !(hi(rlo) > 0.7f) && (!six_seen || (!(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest)));
                     if (__any_sync(0xffffffffu, trig0 || trig1)) {
-                        const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
-                        if (trig0) {
-                            int V; float Rx; bool z;
-                            exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V, Rx, z);
-                            const bool better = (V == 6) && !z && (Rx < b6.bestR);
-                            b6.bestR = better ? Rx : b6.bestR;
-                            b6.bestIdx = better ? j : b6.bestIdx;
-                        }
-                        if (trig1) {
-                            int V; float Rx; bool z;
-                            exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V, Rx, z);
-                            const bool better = (V == 6) && !z && (Rx < b6.bestR);
-                            b6.bestR = better ? Rx : b6.bestR;
-                            b6.bestIdx = better ? j + 1 : b6.bestIdx;
-                        }
+                        // ---- queue the survivors; they are re-evaluated 32 at a time by the whole warp
+                        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
+                        const unsigned below = (1u << lane) - 1u;
+                        if (q0) queue[qn + __popc(b0 & below)] = j;
+                        qn += __popc(b0);
+                        if (q1) queue[qn + __popc(b1 & below)] = j + 1;
+                        qn += __popc(b1);
                         __syncwarp();
-                        wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+                        if (qn >= 32) {
+                            bool saw6 = false;
+                            do {
+                                qn -= 32;
+                                saw6 |= verify_one(det, args.planes, queue[qn + lane], b6);
+                            } while (qn >= 32);
+                            six_seen = six_seen || __any_sync(0xffffffffu, saw6);
+                            wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+                        }
                     }
                 } else {
                     eval_pair<true>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
@@ -472,6 +488,19 @@ GPP_UNROLL(GPP_M6_UNROLL)
             __syncwarp();
         }
 
+        if (kVerified) {
+            bool saw6 = false;                       // the last partial batch of queued survivors
+            if (lane < qn) saw6 = verify_one(det, args.planes, queue[lane], b6);
+            qn = 0;
+            six_seen = six_seen || __any_sync(0xffffffffu, saw6);
+            if (!six_seen) {
+                // no plane has six exact votes: max-votes < 6, the all-six-votes filter does not apply ->
+                // this detection goes to the EXACT second pass (warp-uniform decision)
+                if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
+                continue;
+            }
+            m6 = true;
+        }
         // ---- epilogue: warp reduction, lazy first-masked search, exact recompute of the winner
         int Mw;
         float rbest;

@@ -21,8 +21,11 @@ from .. import _lib
 __all__ = ['PlanePoller', 'get_poller', 'fit_road_planes', 'fit_road_planes_torch', 'fit_road_planes_dlpack',
            'FitRoadPlanes', 'DEFAULT_MODE']
 
-# 'exact' is bit-identical to the oracle's canonical fp32 arithmetic; 'fast' trades that for FMA/MUFU speed
-DEFAULT_MODE = os.environ.get('GPP_MODE', 'exact')
+# 'verified' (default): FAST arithmetic as a filter + EXACT re-evaluation of everything that could win -> the same
+# results as 'exact' (bit-identical to the oracle's canonical fp32 arithmetic) at about twice its speed;
+# 'exact': every hypothesis in the canonical arithmetic; 'fast': FMA/MUFU search only (near-ties may differ);
+# 'f64': FP64 verify mode.
+DEFAULT_MODE = os.environ.get('GPP_MODE', 'verified')
 
 
 def _f32(a):
@@ -276,7 +279,7 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
         keypoints is shaped (num_batch, num_dets, 4, 3) and consists of the 3D location of each of 4 keypoints.
         keyplanes is shaped (num_batch, num_dets, 1, 4) and contains the fitted road plane corresponding to each detection.
         residuals is shaped (num_batch, num_dets) and contains the best 'error of fit' corresponding to the keyplane.
-    Extensions (do not change the default return list): ``mode`` 'exact' | 'fast' | 'f64',
+    Extensions (do not change the default return list): ``mode`` 'verified' | 'exact' | 'fast' | 'f64',
     ``return_index`` appends the winning plane index (int64), ``device`` picks the GPU, ``out`` is a list of
     preallocated result arrays (single shared database only).
     """
