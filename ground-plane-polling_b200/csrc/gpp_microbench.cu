@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(256) microbench_kernel(int trips, float a, flo
                 if (KIND >= 12) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(qv[i]) : "f"(alu[i & 3] + float(i)), "f"(alu[(i + 1) & 3] - float(i)));
-                        asm volatile("mov.b64 %0, {%1, %1};" : "=l"(qb[i]) : "f"(alu[(i + 2) & 3] * float(i + 1)));
+                        const float tv = float(threadIdx.x) * 1e-4f;      // per-thread values: vector registers
+                        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(qv[i]) : "f"(alu[i & 3] + float(i) + tv), "f"(alu[(i + 1) & 3] - float(i) - tv));
+                        asm volatile("mov.b64 %0, {%1, %1};" : "=l"(qb[i]) : "f"(alu[(i + 2) & 3] * float(i + 1) + tv));
                     }
                 }
 #pragma unroll

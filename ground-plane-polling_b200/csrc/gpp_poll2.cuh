@@ -24,6 +24,24 @@ namespace gpp {
 
 typedef unsigned long long u64;
 
+#ifdef GPP_EXP_SCALAR   /* timing experiment only: the same code on scalar instructions */
+struct f2 {
+    float l, h;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi) { return f2{lo, hi}; }
+__device__ __forceinline__ f2 bc(float x) { return f2{x, x}; }
+__device__ __forceinline__ float lo(f2 a) { return a.l; }
+__device__ __forceinline__ float hi(f2 a) { return a.h; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return f2{a.l * b.l, a.h * b.h}; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return f2{a.l + b.l, a.h + b.h}; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return f2{a.l - b.l, a.h - b.h}; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.l, b.l, c.l), fmaf(a.h, b.h, c.h)}; }
+__device__ __forceinline__ f2 from_u64(u64 v) {
+    f2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.l), "=f"(r.h) : "l"(v));
+    return r;
+}
+#else
 // ------------------------------------------------------------------ packed f32x2 primitives
 struct f2 {
     u64 v;
@@ -64,6 +82,8 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
     return r;
 }
+__device__ __forceinline__ f2 from_u64(u64 v) { return f2{v}; }
+#endif
 __device__ __forceinline__ f2 neg2(f2 a) { return pk(-lo(a), -hi(a)); }
 __device__ __forceinline__ f2 abs2(f2 a) { return pk(fabsf(lo(a)), fabsf(hi(a))); }
 
@@ -101,7 +121,11 @@ struct PackFast {
     typedef FastF32 Scalar;
     static __device__ __forceinline__ f2 madd(f2 a, f2 b, f2 c) { return fma2(a, b, c); }
     static __device__ __forceinline__ f2 rcp(f2 a) { return pk(rcp_approx(lo(a)), rcp_approx(hi(a))); }
+#ifdef GPP_EXP_NOSQRT   /* timing experiment only: wrong results */
+    static __device__ __forceinline__ f2 sqrt(f2 a) { return a; }
+#else
     static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(sqrt_approx(lo(a)), sqrt_approx(hi(a))); }
+#endif
 };
 
 // per-detection constants of the packed kernels (warp-uniform scalars)
@@ -384,6 +408,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
         D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
         D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
+
         LaneState<float> st;                 // general mode (max votes not yet known to be 6)
         st.reset(FLT_MAX);
         LaneBest b6;                         // M == 6 mode
@@ -408,7 +433,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     const int j = 2 * (base_pair + p);
                     {
                         PairResult h;
-                        eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                        eval_pair<false>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
                         const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
                         const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
@@ -436,7 +461,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                 if (kVerified) {
                     // ---- filter: a plane can only matter if, within its error margin, it has all six votes,
                     // passes the z-check and scores no worse than the warp's best exact residual so far
-                    eval_pair_fast<true, true>(D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    eval_pair_fast<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                     const f2 R = resid_sum(h);
                     const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
                                      rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
@@ -468,7 +493,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         }
                     }
                 } else {
-                    eval_pair<true>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    eval_pair<true>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                     const f2 R = resid_sum(h);
                     b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
                                lo(h.zc), lo(R), j);
@@ -526,13 +551,13 @@ GPP_UNROLL(GPP_M6_UNROLL)
                 int V0, V1;
                 bool z0, z1;
                 if (kVerified) {
-                    const f2 a01{v0.x}, b01{v0.y}, c01{v1.x}, d01{v1.y};
+                    const f2 a01 = from_u64(v0.x), b01 = from_u64(v0.y), c01 = from_u64(v1.x), d01 = from_u64(v1.y);
                     float Rx;
                     exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V0, Rx, z0);
                     exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V1, Rx, z1);
                 } else {
                     PairResult h;
-                    eval_pair<false>(PP(), D, f2{v0.x}, f2{v0.y}, f2{v1.x}, f2{v1.y}, h);
+                    eval_pair<false>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                     V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
                     V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
                     z0 = lo(h.zc) < 0.0f;

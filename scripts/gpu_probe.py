@@ -17,7 +17,7 @@ from gpp_b200.utils import synthetic  # noqa: E402
 out = {}
 poller = gpp_b200.get_poller(0)
 kinds = {0: 'ffma', 1: 'ffma2', 2: 'fmul+fadd', 3: 'mufu.rcp', 4: 'mufu.rsq', 5: 'ffma+alu', 6: 'sqrt.approx',
-         7: 'fmul2', 8: 'ffma+rcp(4:1)', 9: 'fadd2', 10: 'fmul2|fadd2', 11: 'ffma2|fadd2'}
+         7: 'fmul2', 8: 'ffma+rcp(4:1)', 9: 'fadd2', 10: 'fmul2|fadd2', 11: 'ffma2|fadd2', 12: 'ffma2 3x64b regs', 13: 'ffma2 bcast'}
 mb = {}
 for k, name in kinds.items():
     r = poller.microbench(k)
