@@ -149,6 +149,8 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->d_pairs);
     for (auto &w : h->work) {
         cudaFree(w.list);
+        cudaFree(w.ulist);
+        cudaFree(w.unique);
         cudaFree(w.count);
         if (w.done) cudaEventDestroy(w.done);
     }

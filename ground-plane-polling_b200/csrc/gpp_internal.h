@@ -39,8 +39,10 @@ struct gpp_handle {
     // VERIFIED mode: detections deferred to the EXACT second pass.  A small ring of work lists, each guarded
     // by an event, so that launches in flight on different streams never share one.
     struct WorkSlot {
-        long long *list = nullptr;
-        unsigned int *count = nullptr;
+        long long *list = nullptr;       // deferred detections (VERIFIED second pass)
+        long long *ulist = nullptr;      // rows to poll (not a repeat of the previous row of the image)
+        unsigned char *unique = nullptr; // per row: 1 = polled, 0 = copy of an earlier row
+        unsigned int *count = nullptr;   // [0] deferred count, [1] unique count
         long long cap = 0;
         cudaEvent_t done = nullptr;
         bool used = false;

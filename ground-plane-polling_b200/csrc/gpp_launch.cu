@@ -46,6 +46,60 @@ int build_pairs(gpp_handle *h, cudaStream_t s) {
     return GPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Rows that repeat the previous row of their image bit for bit (FilterDetections pads every image to 100
+// rows with -1, layers/filter_detections.py:170-185) are polled once: mark -> compact -> poll the unique
+// rows -> copy.  Identical inputs give identical outputs, so this changes nothing but the cost.
+// ---------------------------------------------------------------------------------------------------
+__global__ void mark_unique_kernel(const float *__restrict__ boxes, const float *__restrict__ dims,
+                                   const int32_t *__restrict__ orient, long long n_det, int D,
+                                   unsigned char *__restrict__ unique, long long *__restrict__ list,
+                                   unsigned int *__restrict__ count) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool same = true;                                  // out-of-range threads contribute nothing
+    if (m < n_det) {
+        same = (m % D) != 0;
+        if (same) {
+            const unsigned int *b = reinterpret_cast<const unsigned int *>(boxes) + 12 * m;
+            const unsigned int *d = reinterpret_cast<const unsigned int *>(dims) + 3 * m;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) same = same && (b[i] == b[i - 12]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) same = same && (d[i] == d[i - 3]);
+            same = same && (orient[m] == orient[m - 1]);
+        }
+        unique[m] = same ? 0 : 1;
+    }
+    // block-level compaction: one atomic per block reserves a contiguous range of the list
+    __shared__ unsigned int warp_base[9];
+    const unsigned int ballot = __ballot_sync(0xffffffffu, !same);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_base[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int total = 0;
+        for (int w = 0; w < 8; ++w) { const unsigned int c = warp_base[w]; warp_base[w] = total; total += c; }
+        warp_base[8] = total ? atomicAdd(count, total) : 0u;
+    }
+    __syncthreads();
+    if (!same) list[warp_base[8] + warp_base[warp] + __popc(ballot & ((1u << lane) - 1u))] = m;
+}
+
+template <class T>
+__global__ void copy_duplicates_kernel(const unsigned char *__restrict__ unique, long long n_det, T *keypoints,
+                                       T *keyplanes, T *residuals, long long *best) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_det || unique[m]) return;
+    long long r = m - 1;
+    while (!unique[r]) --r;                     // row 0 of every image is unique, so this stays in the image
+#pragma unroll
+    for (int i = 0; i < 12; ++i) keypoints[12 * m + i] = keypoints[12 * r + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) keyplanes[4 * m + i] = keyplanes[4 * r + i];
+    residuals[m] = residuals[r];
+    if (best) best[m] = best[r];
+}
+
 template <class K>
 static int configure_kernel(K kernel, size_t smem, int *occ) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -107,64 +161,46 @@ static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_
     gpp_handle::WorkSlot &w = h->work[h->next_work++ % gpp_handle::kWorkSlots];
     cudaError_t e = cudaSuccess;
     if (!w.done) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
-    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, sizeof(unsigned int));
+    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, 2 * sizeof(unsigned int));
     if (e == cudaSuccess && w.used) e = cudaStreamWaitEvent(s, w.done, 0);   // previous user of this slot
     if (e == cudaSuccess && n_det > w.cap) {
         // cudaMalloc/cudaFree are not stream-ordered: the previous user must be finished on the host side too
         if (w.used) e = cudaEventSynchronize(w.done);
-        if (e == cudaSuccess) { cudaFree(w.list); w.list = nullptr; w.cap = 0; }
+        if (e == cudaSuccess) { cudaFree(w.list); cudaFree(w.ulist); cudaFree(w.unique); w.list = w.ulist = nullptr; w.unique = nullptr; w.cap = 0; }
         if (e == cudaSuccess) e = cudaMalloc(&w.list, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) e = cudaMalloc(&w.ulist, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) e = cudaMalloc(&w.unique, (size_t)n_det);
         if (e == cudaSuccess) w.cap = n_det;
     }
-    if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, sizeof(unsigned int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, 2 * sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "work list setup: %s", cudaGetErrorString(e));
     *out = &w;
     return GPP_OK;
 }
 
-int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
-    if (mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) {
-        PollArgs2<float> b;
-        b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
-        b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
-        b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
-        b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
-        b.defer_list = nullptr; b.defer_count = nullptr;
-        const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
-        if (mode == GPP_MODE_VERIFIED) {
-            int v = GPP_DEFAULT_VARIANT_VERIFIED;
-            if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
-            gpp_handle::WorkSlot *w = nullptr;
-            int rc = reserve_worklist(h, a.n_det, s, &w);
-            if (rc) return rc;
-            b.defer_list = w->list; b.defer_count = w->count;
-            verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
-            // second pass: the deferred detections in the scalar EXACT kernel (count read on the device)
-            PollArgs<float> c = a;
-            c.det_list = w->list; c.det_count = w->count;
-            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
-            h->launches += 1;
-            w->used = true;
-            cudaEventRecord(w->done, s);
-        } else {
-            int v = GPP_DEFAULT_VARIANT_FAST;
-            if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
-            fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
-        }
-    } else {
-        // two detections per warp once every SM has several groups to chew on
-        const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
-        const bool two = a.n_det >= 4 * resident;
-        if (two) {
-            const long long n_groups = (a.n_det + 2 * kWarps - 1) / (2 * kWarps);
-            GPP_K_EXACT2<<<(unsigned)grid_for(h, n_groups, h->occ[1]), kWarps * 32, kSmem1, s>>>(a);
-        } else {
-            const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
-            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(a);
-        }
-    }
+// mark + compact the rows that have to be polled; returns the slot holding the lists
+template <class T>
+static int begin_unique(gpp_handle *h, const PollArgs<T> &a, cudaStream_t s, gpp_handle::WorkSlot **w) {
+    int rc = reserve_worklist(h, a.n_det, s, w);
+    if (rc) return rc;
+    const int threads = 256;
+    const long long blocks = (a.n_det + threads - 1) / threads;
+    mark_unique_kernel<<<(unsigned)blocks, threads, 0, s>>>(a.boxes, a.dims, a.orient, a.n_det, a.dets_per_image,
+                                                           (*w)->unique, (*w)->ulist, (*w)->count + 1);
     h->launches += 1;
-    cudaError_t e = cudaGetLastError();
+    return GPP_OK;
+}
+
+template <class T>
+static int end_unique(gpp_handle *h, const PollArgs<T> &a, cudaStream_t s, gpp_handle::WorkSlot *w) {
+    const int threads = 256;
+    const long long blocks = (a.n_det + threads - 1) / threads;
+    copy_duplicates_kernel<T><<<(unsigned)blocks, threads, 0, s>>>(w->unique, a.n_det, a.keypoints, a.keyplanes,
+                                                                  a.residuals, a.best);
+    h->launches += 1;
+    w->used = true;
+    cudaError_t e = cudaEventRecord(w->done, s);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll kernel launch: %s", cudaGetErrorString(e));
     return GPP_OK;
 }
@@ -237,13 +273,63 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
     return GPP_OK;
 }
 
-int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a, cudaStream_t s) {
+int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaStream_t s) {
+    gpp_handle::WorkSlot *w = nullptr;
+    int rc = begin_unique(h, a_in, s, &w);
+    if (rc) return rc;
+    PollArgs<float> a = a_in;
+    a.det_list = w->ulist; a.det_count = w->count + 1;
+    // grids are sized for the worst case (every row unique); the kernels read the real count on the device
+    if (mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) {
+        PollArgs2<float> b;
+        b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
+        b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
+        b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
+        b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
+        b.defer_list = nullptr; b.defer_count = nullptr;
+        b.det_list = a.det_list; b.det_count = a.det_count;
+        const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+        if (mode == GPP_MODE_VERIFIED) {
+            int v = GPP_DEFAULT_VARIANT_VERIFIED;
+            if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
+            b.defer_list = w->list; b.defer_count = w->count;
+            verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
+            // second pass: the deferred detections in the scalar EXACT kernel (count read on the device)
+            PollArgs<float> c = a;
+            c.det_list = w->list; c.det_count = w->count;
+            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
+            h->launches += 1;
+        } else {
+            int v = GPP_DEFAULT_VARIANT_FAST;
+            if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
+            fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
+        }
+    } else {
+        // two detections per warp once every SM has several groups to chew on
+        const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
+        const bool two = a.n_det >= 4 * resident;
+        if (two) {
+            const long long n_groups = (a.n_det + 2 * kWarps - 1) / (2 * kWarps);
+            GPP_K_EXACT2<<<(unsigned)grid_for(h, n_groups, h->occ[1]), kWarps * 32, kSmem1, s>>>(a);
+        } else {
+            const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(a);
+        }
+    }
+    h->launches += 1;
+    return end_unique(h, a, s, w);
+}
+
+int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a_in, cudaStream_t s) {
+    gpp_handle::WorkSlot *w = nullptr;
+    int rc = begin_unique(h, a_in, s, &w);
+    if (rc) return rc;
+    PollArgs<double> a = a_in;
+    a.det_list = w->ulist; a.det_count = w->count + 1;
     const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
     GPP_K_F64<<<(unsigned)grid_for(h, n_groups, h->occ[2]), kWarps * 32, kSmem64, s>>>(a);
     h->launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll_kernel<f64> launch: %s", cudaGetErrorString(e));
-    return GPP_OK;
+    return end_unique(h, a, s, w);
 }
 
 }  // namespace gpp

@@ -321,6 +321,10 @@ struct PollArgs2 {
     // second pass (scalar EXACT kernel over this work list) instead of slowing their CTA down
     long long *defer_list;
     unsigned int *defer_count;
+    // optional work list: process det_list[0 .. *det_count) instead of 0 .. n_det (rows that repeat the
+    // previous row of their image -- FilterDetections' -1 padding -- are computed once and copied)
+    const long long *det_list;
+    const unsigned int *det_count;
 };
 
 // kTile planes per smem tile (multiple of 64), one detection per warp.
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     const int N = args.n_planes;
     const int NP = args.n_pairs_padded;
     const int n_tiles = (NP + kTilePairs - 1) / kTilePairs;
-    const long long n_groups = (args.n_det + kWarps - 1) / kWarps;
+    const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
+    const long long n_groups = (n_work + kWarps - 1) / kWarps;
     const long long my_groups = (n_groups > blockIdx.x) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total_tiles = my_groups * n_tiles;
 
@@ -396,8 +401,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     long long it = 0;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
-        const long long m = g * kWarps + warp;
-        const long long mm = m < args.n_det ? m : args.n_det - 1;
+        const long long w_id = g * kWarps + warp;
+        long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
+        if (args.det_list) mm = args.det_list[mm];
+        const long long m = w_id < n_work ? mm : args.n_det;       // >= n_det: nothing is written
         DetConst D;
         Detection<ExactF32> det;             // same registers as D (the copies below are free)
         load_detection<ExactF32, ExactF32>(det, args.boxes + 12 * mm, args.dims + 3 * mm,

@@ -92,3 +92,20 @@ def test_margin_bounds_the_fast_vs_exact_deviation(poller):
             ratio = np.abs(fr[rel] - er[rel]) / fm[rel]
             worst = max(worst, float(ratio.max()) if ratio.size else 0.0)
     assert worst < 0.25, worst
+
+
+def test_padding_rows_are_polled_once_and_copied(gpp):
+    """FilterDetections pads every image to D rows with -1: the repeats are computed once per image and
+    copied, and still equal the oracle bit for bit in every mode."""
+    planes = load_planes('22k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(6, 100, planes, seed=303, n_valid=13)
+    boxes[2] = -1.0; dims[2] = -1.0; orient[2] = -1            # an image without any detection
+    boxes[3, 50] = boxes[3, 12]; dims[3, 50] = dims[3, 12]; orient[3, 50] = orient[3, 12]   # a valid row among padding
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    for mode in ('verified', 'exact'):
+        got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True)
+        _same(got, want)
+    got64 = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64', return_index=True)
+    want64 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True, dtype=np.float64)
+    assert np.array_equal(got64[3], want64[3])
+    assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
