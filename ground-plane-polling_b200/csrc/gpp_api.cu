@@ -491,7 +491,8 @@ int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int 
 
 int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm) {
     if (!h) return set_error(GPP_EINVAL, "gpp_debug_set_config: handle is NULL");
-    h->force_variant = variant;
+    h->force_variant = variant % 100;
+    h->force_split = variant >= 200 ? -1 : (variant >= 100 ? 1 : 0);   // +100: force split kernels, +200: forbid
     h->force_ctas_per_sm = ctas_per_sm;
     return GPP_OK;
 }

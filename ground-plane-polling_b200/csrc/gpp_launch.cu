@@ -118,16 +118,22 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
 }
 
 constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t) +
-                          sizeof(int) * kWarps * kVerifyQueue;
-constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t);
+                          sizeof(int) * kWarps * kVerifyQueue + 2 * kWarps * sizeof(WarpPartial<float>);
+constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t) +
+                           2 * kWarps * sizeof(WarpPartial<double>);
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
+#define GPP_K_F64_SPLIT poll_kernel<ExactF64, kWarps, 1, kTile64, kStages, true>
 
 // EXACT fp32 mode runs the scalar kernel (gpp_poll.cuh): ptxas 12.9 contracts a packed mul.rn.f32x2 feeding a
 // packed add.rn.f32x2 into FFMA2 even with explicit .rn (checked in SASS), which would break the FMA-free
 // canonical arithmetic, so the packed kernel is used for the FAST mode only.
 #define GPP_K_EXACT1 poll_kernel<ExactF32, kWarps, 1, kTile32, kStages>
 #define GPP_K_EXACT2 poll_kernel<ExactF32, kWarps, 2, kTile32, kStages>
-constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t);
+#define GPP_K_EXACT_SPLIT poll_kernel<ExactF32, kWarps, 1, kTile32, kStages, true>
+#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, false, true>
+#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, true, true>
+constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
+                          2 * kWarps * sizeof(WarpPartial<float>);
 
 // FAST kernel variants: v = 0..2 <-> __launch_bounds__(256, 2 / 3 / 4) i.e. <= 128 / 80 / 64 registers
 typedef void (*Poll2Fn)(const PollArgs2<float>);
@@ -154,7 +160,17 @@ int configure_kernels(gpp_handle *h) {
     for (int v = 0; v < 2; ++v)
         if ((rc = configure_kernel(verified_variant(v), kSmem2, &h->occ3[v]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64, kSmem64, &h->occ[2]))) return rc;
+    if ((rc = configure_kernel(GPP_K_EXACT_SPLIT, kSmem1, &h->occ_split[0]))) return rc;
+    if ((rc = configure_kernel(GPP_K_FAST_SPLIT, kSmem2, &h->occ_split[1]))) return rc;
+    if ((rc = configure_kernel(GPP_K_VERIFIED_SPLIT, kSmem2, &h->occ_split[2]))) return rc;
+    if ((rc = configure_kernel(GPP_K_F64_SPLIT, kSmem64, &h->occ_split[3]))) return rc;
     return GPP_OK;
+}
+
+// small batches: fewer detections than a few per resident CTA -> one detection per CTA, planes split over warps
+static bool use_split(const gpp_handle *h, long long n_det) {
+    if (h->force_split) return h->force_split > 0;
+    return n_det < 4LL * h->sm_count * 3;
 }
 
 static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_handle::WorkSlot **out) {
@@ -288,22 +304,32 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
         b.defer_list = nullptr; b.defer_count = nullptr;
         b.det_list = a.det_list; b.det_count = a.det_count;
-        const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+        const bool split = use_split(h, a.n_det);
+        const long long n_groups = split ? a.n_det : (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
             if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
             b.defer_list = w->list; b.defer_count = w->count;
-            verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
             // second pass: the deferred detections in the scalar EXACT kernel (count read on the device)
             PollArgs<float> c = a;
             c.det_list = w->list; c.det_count = w->count;
-            GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
+            if (split) {
+                GPP_K_VERIFIED_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[2]), kWarps * 32, kSmem2, s>>>(b);
+                GPP_K_EXACT_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[0]), kWarps * 32, kSmem1, s>>>(c);
+            } else {
+                verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
+                GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
+            }
             h->launches += 1;
+        } else if (split) {
+            GPP_K_FAST_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[1]), kWarps * 32, kSmem2, s>>>(b);
         } else {
             int v = GPP_DEFAULT_VARIANT_FAST;
             if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
             fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
         }
+    } else if (use_split(h, a.n_det)) {
+        GPP_K_EXACT_SPLIT<<<(unsigned)grid_for(h, a.n_det, h->occ_split[0]), kWarps * 32, kSmem1, s>>>(a);
     } else {
         // two detections per warp once every SM has several groups to chew on
         const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
@@ -326,8 +352,12 @@ int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a_in, cudaStream_t s)
     if (rc) return rc;
     PollArgs<double> a = a_in;
     a.det_list = w->ulist; a.det_count = w->count + 1;
-    const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
-    GPP_K_F64<<<(unsigned)grid_for(h, n_groups, h->occ[2]), kWarps * 32, kSmem64, s>>>(a);
+    if (use_split(h, a.n_det)) {
+        GPP_K_F64_SPLIT<<<(unsigned)grid_for(h, a.n_det, h->occ_split[3]), kWarps * 32, kSmem64, s>>>(a);
+    } else {
+        const long long n_groups = (a.n_det + kWarps - 1) / kWarps;
+        GPP_K_F64<<<(unsigned)grid_for(h, n_groups, h->occ[2]), kWarps * 32, kSmem64, s>>>(a);
+    }
     h->launches += 1;
     return end_unique(h, a, s, w);
 }

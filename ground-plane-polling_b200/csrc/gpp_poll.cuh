@@ -111,17 +111,29 @@ __device__ __forceinline__ double warp_min_first(double v, int &idx) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// partial result of one warp when the warps of a CTA split the planes of ONE detection (small batches)
+template <class T>
+struct WarpPartial {
+    T r;
+    int M, idx;
+};
+
 // kWarps warps per CTA, kDpw detections per warp in flight, kTile planes per smem tile, kStages ring depth.
-template <class P, int kWarps, int kDpw, int kTile, int kStages>
+// kSplit: small-batch variant -- the CTA works on one detection, warp w takes the rows r = w (mod kWarps) of
+// every tile and the partial arg-mins are merged through shared memory (kDpw must be 1).
+template <class P, int kWarps, int kDpw, int kTile, int kStages, bool kSplit = false>
 __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typename P::T> args) {
     typedef typename P::T T;
     typedef typename P::T4 T4;
-    constexpr int kGroup = kWarps * kDpw;            // detections per CTA pass over the database
+    static_assert(!kSplit || kDpw == 1, "the split variant handles one detection per CTA");
+    constexpr int kGroup = kSplit ? 1 : kWarps * kDpw;   // detections per CTA pass over the database
+    constexpr int kRowStep = kSplit ? kWarps : 1;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T4 *tiles = reinterpret_cast<T4 *>(smem_raw);                                  // kStages * kTile
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(T4) * kStages * kTile);
     uint64_t *empty_bar = full_bar + kStages;
+    WarpPartial<T> *partial = reinterpret_cast<WarpPartial<T> *>(empty_bar + kStages);   // [2][kWarps], kSplit only
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
         // ---- per-detection prologue (warp-uniform; fit_road_planes.py:66-72, :80-83)
 #pragma unroll
         for (int q = 0; q < kDpw; ++q) {
-            long long m = g * kGroup + (long long)warp * kDpw + q;
+            long long m = kSplit ? g : g * kGroup + (long long)warp * kDpw + q;
             long long mm = m < n_work ? m : n_work - 1;                   // tail warps redo the last one
             if (args.det_list) mm = args.det_list[mm];
             det_id[q] = m < n_work ? mm : -1;
@@ -183,9 +195,9 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
             const int cnt = min(kTile, N - t * kTile);
             const int base = t * kTile;
             const int full_rows = cnt >> 5;
-            int r = 0;
+            int r = kSplit ? warp : 0;
 #pragma unroll 1
-            for (; r < full_rows; ++r) {
+            for (; r < full_rows; r += kRowStep) {
                 const int jj = (r << 5) + lane;
                 const T4 pl = tile[jj];
 #pragma unroll
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
                     st[q].update(V, R, zneg, base + jj, highest);
                 }
             }
-            if ((cnt & 31) != 0) {                   // ragged last row of the last tile
+            if ((cnt & 31) != 0 && (!kSplit || r == full_rows)) {   // ragged last row of the last tile
                 const int jj = (r << 5) + lane;
                 if (jj < cnt) {
                     const T4 pl = tile[jj];
@@ -224,10 +236,22 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
         // ---- per-detection epilogue: warp reduction, lazy first-masked search, exact recompute, store
 #pragma unroll
         for (int q = 0; q < kDpw; ++q) {
-            const int Mw = __reduce_max_sync(0xffffffffu, st[q].M);
+            int Mw = __reduce_max_sync(0xffffffffu, st[q].M);
             T r = (st[q].M == Mw) ? st[q].bestR : highest;
             int idx = st[q].bestIdx;
             r = warp_min_first(r, idx);
+            if (kSplit) {
+                // merge the warps' partial results (double-buffered by group parity: one barrier per group)
+                WarpPartial<T> *buf = partial + ((g / gridDim.x) & 1) * kWarps;
+                if (lane == 0) { buf[warp].r = r; buf[warp].M = Mw; buf[warp].idx = idx; }
+                __syncthreads();
+                if (warp != 0) continue;
+                const int Ml = lane < kWarps ? buf[lane].M : -1;
+                Mw = __reduce_max_sync(0xffffffffu, Ml);
+                r = (lane < kWarps && Ml == Mw) ? buf[lane].r : highest;
+                idx = lane < kWarps ? buf[lane].idx : 0;
+                r = warp_min_first(r, idx);
+            }
             const bool have_cand = r < highest;
             bool sentinel = false;
             if (!(r < T(100))) {

@@ -352,9 +352,11 @@ __device__ __forceinline__ bool verify_one(const Detection<ExactF32> &de, const 
 // kVerified: FAST arithmetic is only a filter -- every hypothesis that could be the arg-min within the error
 // margin is re-evaluated in the EXACT arithmetic and all selection state is kept in exact values, so the
 // result equals the EXACT mode's (see the header comment of the verified path below).
-template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, bool kVerified = false>
+// kSplit: small-batch variant (one detection per CTA, warp w takes the rows r = w (mod kWarps) of every tile).
+template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, bool kVerified = false, bool kSplit = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
     constexpr int kTilePairs = kTile / 2;
+    constexpr int kRowStep = kSplit ? kWarps : 1;
     constexpr uint32_t kPairBytes = 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ulonglong2 *tiles = reinterpret_cast<ulonglong2 *>(smem_raw);             // 2 x ulonglong2 per pair
@@ -362,6 +364,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     uint64_t *empty_bar = full_bar + kStages;
     // VERIFIED: per-warp queue of plane indices that survived the fast filter (at most 31 + 64 entries)
     int *queue = reinterpret_cast<int *>(empty_bar + kStages) + (threadIdx.x >> 5) * kVerifyQueue;
+    WarpPartial<float> *partial = reinterpret_cast<WarpPartial<float> *>(
+        reinterpret_cast<int *>(empty_bar + kStages) + kWarps * kVerifyQueue);              // [2][kWarps], kSplit only
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     const int NP = args.n_pairs_padded;
     const int n_tiles = (NP + kTilePairs - 1) / kTilePairs;
     const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
-    const long long n_groups = (n_work + kWarps - 1) / kWarps;
+    const long long n_groups = kSplit ? n_work : (n_work + kWarps - 1) / kWarps;
     const long long my_groups = (n_groups > blockIdx.x) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total_tiles = my_groups * n_tiles;
 
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     long long it = 0;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
-        const long long w_id = g * kWarps + warp;
+        const long long w_id = kSplit ? g : g * kWarps + warp;
         long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
         if (args.det_list) mm = args.det_list[mm];
         const long long m = w_id < n_work ? mm : args.n_det;       // >= n_det: nothing is written
@@ -431,10 +435,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
             const ulonglong2 *tile = tiles + size_t(s) * kTilePairs * 2;
             const int rows = min(kTilePairs, NP - t * kTilePairs) >> 5;
             const int base_pair = t * kTilePairs;
-            int r = 0;
+            int r = kSplit ? warp : 0;
             if (!kVerified && !m6) {
 #pragma unroll 1
-                for (; r < rows; ++r) {
+                for (; r < rows; r += kRowStep) {
                     const int p = (r << 5) + lane;
                     const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                     const int j = 2 * (base_pair + p);
@@ -447,9 +451,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                         st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
                         st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
                     }
-                    if ((r & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                    if (((r / kRowStep) & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
                         m6 = true;                               // warp-uniform decision
-                        ++r;
+                        r += kRowStep;
                         break;
                     }
                 }
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                 }
             }
 GPP_UNROLL(GPP_M6_UNROLL)
-            for (; r < rows; ++r) {
+            for (; r < rows; r += kRowStep) {
                 const int p = (r << 5) + lane;
                 const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                 PairResult h;
@@ -525,13 +529,18 @@ GPP_UNROLL(GPP_M6_UNROLL)
             if (lane < qn) saw6 = verify_one(det, args.planes, queue[lane], b6);
             qn = 0;
             six_seen = six_seen || __any_sync(0xffffffffu, saw6);
-            if (!six_seen) {
-                // no plane has six exact votes: max-votes < 6, the all-six-votes filter does not apply ->
-                // this detection goes to the EXACT second pass (warp-uniform decision)
-                if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
-                continue;
+            if (!kSplit) {
+                if (!six_seen) {
+                    // no plane has six exact votes: max-votes < 6, the all-six-votes filter does not apply ->
+                    // this detection goes to the EXACT second pass (warp-uniform decision)
+                    if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
+                    continue;
+                }
+                m6 = true;
+            } else {
+                m6 = six_seen;                       // this warp's share; merged below
+                if (!m6) st.reset(FLT_MAX);          // contributes M = -1, no candidate
             }
-            m6 = true;
         }
         // ---- epilogue: warp reduction, lazy first-masked search, exact recompute of the winner
         int Mw;
@@ -547,6 +556,22 @@ GPP_UNROLL(GPP_M6_UNROLL)
             idx = st.bestIdx;
         }
         rbest = warp_min_first(rbest, idx);
+        if (kSplit) {
+            // merge the warps' partial results (double-buffered by group parity: one barrier per group)
+            WarpPartial<float> *buf = partial + ((g / gridDim.x) & 1) * kWarps;
+            if (lane == 0) { buf[warp].r = rbest; buf[warp].M = Mw; buf[warp].idx = idx; }
+            __syncthreads();
+            if (warp != 0) continue;
+            const int Ml = lane < kWarps ? buf[lane].M : -1;
+            Mw = __reduce_max_sync(0xffffffffu, Ml);
+            rbest = (lane < kWarps && Ml == Mw) ? buf[lane].r : FLT_MAX;
+            idx = lane < kWarps ? buf[lane].idx : 0;
+            rbest = warp_min_first(rbest, idx);
+            if (kVerified && Mw < 6) {               // no warp saw a six-vote plane: EXACT second pass
+                if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
+                continue;
+            }
+        }
         const bool have_cand = rbest < FLT_MAX;
         bool sentinel = false;
         if (!(rbest < 100.0f)) {

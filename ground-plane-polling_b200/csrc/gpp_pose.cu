@@ -118,9 +118,106 @@ __global__ void pose_kernel(const float *__restrict__ keypoints, const float *__
     dims_out[3 * i + 2] = l;
 }
 
+// KITTI record of one posed detection -- the per-detection arithmetic of the reference's KITTI writer
+// (bin/run_network.py:295-330): R = Rodrigues(angles); the 8 box corners (label_prep/computeBox3D.m
+// convention) rotated and translated; Y = max corner y, h = Y - min corner y; r_y = angles[1] wrapped to
+// [-pi, pi); alpha = r_y + atan2(z, x) + 1.5 pi wrapped the same way.  out = (alpha, h, Y, r_y).
+__device__ __forceinline__ double wrap_pi(double a) {
+    const double two_pi = 6.283185307179586476925286766559;
+    a = fmod(a, two_pi);
+    if (a < 0) a += two_pi;                                    // python's % returns a value in [0, 2 pi)
+    if (a >= 3.14159265358979323846) a -= two_pi;
+    return a;
+}
+
+__global__ void kitti_kernel(const float *__restrict__ locations, const float *__restrict__ angles,
+                             const float *__restrict__ dims, long long n, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double rx = angles[3 * i], ry = angles[3 * i + 1], rz = angles[3 * i + 2];
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    // second row of the rotation matrix (only the y coordinates of the corners are needed)
+    double R10, R11, R12;
+    if (theta < 2.220446049250313e-16) {
+        R10 = 0.0; R11 = 1.0; R12 = 0.0;
+    } else {
+        const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+        const double ux = rx * it, uy = ry * it, uz = rz * it;
+        R10 = c1 * uy * ux + s * uz;
+        R11 = c + c1 * uy * uy;
+        R12 = c1 * uy * uz - s * ux;
+    }
+    const double h = dims[3 * i], w = dims[3 * i + 1], l = dims[3 * i + 2];
+    const double xs[8] = {l / 2, l / 2, -l / 2, -l / 2, l / 2, l / 2, -l / 2, -l / 2};
+    const double ys[8] = {0, 0, 0, 0, -h, -h, -h, -h};
+    const double zs[8] = {w / 2, -w / 2, -w / 2, w / 2, w / 2, -w / 2, -w / 2, w / 2};
+    const double ly = locations[3 * i + 1];
+    double ymax = -1e300, ymin = 1e300;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double y = R10 * xs[k] + R11 * ys[k] + R12 * zs[k] + ly;
+        ymax = fmax(ymax, y);
+        ymin = fmin(ymin, y);
+    }
+    const double r_y = wrap_pi(ry);
+    const double alpha = wrap_pi(r_y + atan2((double)locations[3 * i + 2], (double)locations[3 * i]) + 4.71238898038468985769);
+    out[4 * i + 0] = (float)alpha;
+    out[4 * i + 1] = (float)(ymax - ymin);
+    out[4 * i + 2] = (float)ymax;
+    out[4 * i + 3] = (float)r_y;
+}
+
 }  // namespace gpp
 
 extern "C" {
+
+int gpp_kitti_device(gpp_handle *h, const float *locations, const float *angles, const float *dimensions, long n,
+                     float *out, void *stream) {
+    if (!h || n < 0) return gpp::set_error(GPP_EINVAL, "gpp_kitti_device: bad argument");
+    if (n == 0) return GPP_OK;
+    if (!locations || !angles || !dimensions || !out)
+        return gpp::set_error(GPP_EINVAL, "gpp_kitti_device: NULL array argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    const int threads = 128;
+    gpp::kitti_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        locations, angles, dimensions, n, out);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) return gpp::set_error(GPP_ECUDA, "kitti_kernel launch: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+int gpp_kitti_host(gpp_handle *h, const float *locations, const float *angles, const float *dimensions, long n,
+                   float *out) {
+    if (!h || n < 0) return gpp::set_error(GPP_EINVAL, "gpp_kitti_host: bad argument");
+    if (n == 0) return GPP_OK;
+    if (!locations || !angles || !dimensions || !out)
+        return gpp::set_error(GPP_EINVAL, "gpp_kitti_host: NULL array argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    float *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(float) * 13 * (size_t)n);
+    int rc = GPP_OK;
+    if (e == cudaSuccess) {
+        cudaStream_t s = h->streams[0];
+        float *d_loc = d, *d_ang = d + 3 * (size_t)n, *d_dim = d + 6 * (size_t)n, *d_out = d + 9 * (size_t)n;
+        e = cudaMemcpyAsync(d_loc, locations, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ang, angles, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dim, dimensions, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) rc = gpp_kitti_device(h, d_loc, d_ang, d_dim, n, d_out, s);
+        if (e == cudaSuccess && rc == GPP_OK) e = cudaMemcpyAsync(out, d_out, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == GPP_OK) e = cudaStreamSynchronize(s);
+    }
+    cudaFree(d);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (rc != GPP_OK) return rc;
+    if (e != cudaSuccess) return gpp::set_error(GPP_ECUDA, "gpp_kitti_host: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
 
 int gpp_pose_device(gpp_handle *h, const float *keypoints, const float *dimensions,
                     const int32_t *orientations, long n, float *locations, float *angles,

@@ -115,6 +115,15 @@ int gpp_pose_device(gpp_handle *h, const float *keypoints, const float *dimensio
                     const int32_t *orientations, long n, float *locations, float *angles,
                     float *dimensions_out, void *stream);
 
+/* KITTI record of posed detections -- the per-detection arithmetic of the reference's KITTI writer
+ * (run_network.py:295-330): out[i] = (alpha, h, Y, r_y) where R = Rodrigues(angles[i]), Y / h are the bottom
+ * and the height of the rotated 8-corner box, r_y = angles[i][1] wrapped to [-pi, pi) and alpha the observation
+ * angle.  locations / angles / dimensions: n*3 floats (the outputs of gpp_pose_*), out: n*4 floats. */
+int gpp_kitti_host(gpp_handle *h, const float *locations, const float *angles, const float *dimensions, long n,
+                   float *out);
+int gpp_kitti_device(gpp_handle *h, const float *locations, const float *angles, const float *dimensions, long n,
+                     float *out, void *stream);
+
 /* Measurement helpers (bench.py): time of the last gpp_fit_* polling kernel(s) in milliseconds, measured
  * with CUDA events on the launching stream (valid after the stream has been synchronised); number of
  * kernels launched by this handle so far. */
@@ -133,8 +142,9 @@ int64_t gpp_launch_count(const gpp_handle *h);
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
 
 /* Tuning hook (benchmarks only): `variant` 2 / 3 / 4 selects the fp32 kernel compiled for that many resident
- * CTAs per SM (register budget 128 / 80 / 64; 0 = built-in default), `ctas_per_sm` sizes the persistent grid
- * (0 = occupancy maximum). */
+ * CTAs per SM (register budget 128 / 80 / 64; 0 = built-in default); +100 forces, +200 forbids the small-batch
+ * kernels (one detection per CTA, planes split over the warps; default: automatic by batch size);
+ * `ctas_per_sm` sizes the persistent grid (0 = occupancy maximum). */
 int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
 
 /* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same

@@ -48,3 +48,45 @@ def test_pose_device_entry(gpp):
     hl, ha, hd = gpp.recover_pose(out[0].cpu().numpy(), dims.reshape(-1, 3), orient.reshape(-1))
     assert np.array_equal(loc.cpu().numpy(), hl) and np.array_equal(ang.cpu().numpy(), ha)
     assert np.array_equal(dout.cpu().numpy(), hd)
+
+
+def test_kitti_records_match_reference_writer(gpp):
+    from oracle.kitti_ref import kitti_records_ref
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 100, planes, seed=93)
+    kp, kpl, res = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes)
+    wloc, wang, wdims = pose_ref(kp.reshape(-1, 12), dims.reshape(-1, 3).copy(), orient.reshape(-1))
+    ok = np.isfinite(wang).all(1) & np.isfinite(wloc).all(1)
+    got = gpp.kitti_records(wloc[ok], wang[ok], wdims[ok])
+    want = kitti_records_ref(wloc[ok], wang[ok], wdims[ok])
+    assert got.shape == want.shape
+    # angles (alpha, r_y) compared on the circle, lengths (h, Y) relatively
+    assert np.all(np.abs(_wrap(got[:, 0] - want[:, 0])) <= RTOL * np.pi)
+    assert np.all(np.abs(_wrap(got[:, 3] - want[:, 3])) <= RTOL * np.pi)
+    assert np.allclose(got[:, 1], want[:, 1], rtol=RTOL, atol=1e-5)
+    assert np.allclose(got[:, 2], want[:, 2], rtol=RTOL, atol=1e-4)
+
+
+def test_postprocess_image_mirrors_the_driver(gpp):
+    """run_network.py:113-287 for one image: score filter + sort, unscale, pose, KITTI record."""
+    from oracle.kitti_ref import kitti_records_ref
+    planes = load_planes('1k')
+    rng = np.random.default_rng(5)
+    boxes, dims, orient, P_inv = synthetic.synth_detections(1, 100, planes, seed=94, n_valid=40)
+    scores = np.where(np.arange(100) < 40, rng.uniform(0.0, 1.0, 100), -1.0).astype(np.float32)
+    labels = np.where(np.arange(100) < 40, 0, -1).astype(np.int32)
+    kp, kpl, res = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes)
+    scale = 1333.0 / 1242.0
+    out = gpp.postprocess_image(boxes[0], dims[0], scores, labels, orient[0], kp[0], kpl[0], res[0], scale)
+    keep = np.where(scores > 0.05)[0]
+    keep = keep[np.argsort(-scores[keep])][:100]
+    assert np.array_equal(out['scores'], scores[keep])
+    assert np.allclose(out['boxes'], boxes[0][keep][:, :4] / np.float32(scale))
+    wloc, wang, wdims = pose_ref(kp[0].reshape(-1, 12)[keep], dims[0][keep].copy(), orient[0][keep])
+    assert np.allclose(out['locations'], wloc, rtol=1e-4, atol=1e-4)
+    assert np.allclose(out['dimensions'], wdims, rtol=1e-4, atol=0)
+    want = kitti_records_ref(wloc, wang, wdims)
+    assert np.allclose(out['kitti'][:, 1:3], want[:, 1:3], rtol=1e-4, atol=1e-4)
+    lines = gpp.kitti.format_kitti_lines(out['boxes'], out['dimensions'], out['locations'], out['scores'],
+                                         out['kitti'], (1242, 375))
+    assert len(lines) == len(keep) and lines[0].startswith('Car -1 -1 ')

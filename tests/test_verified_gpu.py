@@ -109,3 +109,27 @@ def test_padding_rows_are_polled_once_and_copied(gpp):
     want64 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True, dtype=np.float64)
     assert np.array_equal(got64[3], want64[3])
     assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize('force', [100, 200])
+def test_small_batch_split_kernels_equal_oracle(gpp, poller, force):
+    """One detection per CTA with the planes split over the warps (small batches) vs the batch kernels: both
+    forced on the same inputs, every mode, incl. ragged N, padding rows and detections without six votes."""
+    planes = load_planes('22k')[:5003]
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 40, planes, seed=404, n_valid=33)
+    dims = dims.copy()
+    dims[1, :10, 1] *= 1.7
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    want64 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True, dtype=np.float64)
+    poller.debug_set_config(force, 0)
+    try:
+        for mode in ('exact', 'verified'):
+            _same(gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True), want)
+        got64 = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64', return_index=True)
+        fast = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='fast', return_index=True)
+    finally:
+        poller.debug_set_config(0, 0)
+    assert np.array_equal(got64[3], want64[3])
+    assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
+    valid = orient >= 0          # padding rows are degenerate (all key-points equal): pure rounding-noise ties
+    assert np.mean(fast[3][valid] == want[3][valid]) > 0.97
