@@ -130,8 +130,10 @@ constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * s
 #define GPP_K_EXACT1 poll_kernel<ExactF32, kWarps, 1, kTile32, kStages>
 #define GPP_K_EXACT2 poll_kernel<ExactF32, kWarps, 2, kTile32, kStages>
 #define GPP_K_EXACT_SPLIT poll_kernel<ExactF32, kWarps, 1, kTile32, kStages, true>
-#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, false, true>
-#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, true, true>
+#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 0, true>
+#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 1, true>
+#define GPP_K_GENERAL poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 2, false>
+#define GPP_K_GENERAL_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 2, true>
 constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
                           2 * kWarps * sizeof(WarpPartial<float>);
 
@@ -146,8 +148,8 @@ static Poll2Fn fast_variant(int v) {
 }
 static Poll2Fn verified_variant(int v) {
     switch (v) {
-        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2, true>;
-        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, true>;
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2, 1>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 1>;
     }
 }
 
@@ -164,6 +166,8 @@ int configure_kernels(gpp_handle *h) {
     if ((rc = configure_kernel(GPP_K_FAST_SPLIT, kSmem2, &h->occ_split[1]))) return rc;
     if ((rc = configure_kernel(GPP_K_VERIFIED_SPLIT, kSmem2, &h->occ_split[2]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64_SPLIT, kSmem64, &h->occ_split[3]))) return rc;
+    if ((rc = configure_kernel(GPP_K_GENERAL, kSmem2, &h->occ_general[0]))) return rc;
+    if ((rc = configure_kernel(GPP_K_GENERAL_SPLIT, kSmem2, &h->occ_general[1]))) return rc;
     return GPP_OK;
 }
 
@@ -257,10 +261,15 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
         const f2 R = resid_sum(h);
         const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
         const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-        votes[2 * p] = V0; resid[2 * p] = lo(R); zneg[2 * p] = lo(h.zc) < 0.0f ? 1 : 0;
+        // votes: fast count + 16 x the count that is possible within the margin (the VERIFIED filters' test);
+        // zneg: fast z-check + 2 x "may pass the z-check within the margin"
+        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
+        votes[2 * p] = V0 + 16 * loose_votes(h, false); resid[2 * p] = lo(R);
+        zneg[2 * p] = (lo(h.zc) < 0.0f ? 1 : 0) + (!(lo(zhi) < 0.0f) ? 2 : 0);
         if (margin) margin[2 * p] = lo(h.m);
         if (2 * p + 1 < a.n_planes) {
-            votes[2 * p + 1] = V1; resid[2 * p + 1] = hi(R); zneg[2 * p + 1] = hi(h.zc) < 0.0f ? 1 : 0;
+            votes[2 * p + 1] = V1 + 16 * loose_votes(h, true); resid[2 * p + 1] = hi(R);
+            zneg[2 * p + 1] = (hi(h.zc) < 0.0f ? 1 : 0) + (!(hi(zhi) < 0.0f) ? 2 : 0);
             if (margin) margin[2 * p + 1] = hi(h.m);
         }
     }
@@ -310,15 +319,17 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
             if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
             b.defer_list = w->list; b.defer_count = w->count;
-            // second pass: the deferred detections in the scalar EXACT kernel (count read on the device)
-            PollArgs<float> c = a;
+            // second pass: the deferred detections (max-votes < 6) through the general filter; the count is
+            // read on the device, the grid is sized for the worst case
+            PollArgs2<float> c = b;
             c.det_list = w->list; c.det_count = w->count;
+            c.defer_list = nullptr; c.defer_count = nullptr;
             if (split) {
                 GPP_K_VERIFIED_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[2]), kWarps * 32, kSmem2, s>>>(b);
-                GPP_K_EXACT_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[0]), kWarps * 32, kSmem1, s>>>(c);
+                GPP_K_GENERAL_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_general[1]), kWarps * 32, kSmem2, s>>>(c);
             } else {
                 verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
-                GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(c);
+                GPP_K_GENERAL<<<(unsigned)grid_for(h, n_groups, h->occ_general[0]), kWarps * 32, kSmem2, s>>>(c);
             }
             h->launches += 1;
         } else if (split) {

@@ -349,12 +349,45 @@ __device__ __forceinline__ bool verify_one(const Detection<ExactF32> &de, const 
     return V == 6;                               // max-votes == 6 is established (z-check or not)
 }
 
+// VERIFIED, general filter: exact re-evaluation with the full (max-votes, residual, index) bookkeeping
+__device__ __forceinline__ void verify_general(const Detection<ExactF32> &de, const float4 *__restrict__ planes, int j,
+                                               LaneState<float> &st) {
+    const float4 pl = planes[j];
+    int V; float R; bool z;
+    exact_one(de, pl.x, pl.y, pl.z, pl.w, V, R, z);
+    const bool cand = !z && (R < FLT_MAX);                     // NaN / >= highest can never win
+    if (V > st.M) {
+        st.M = V;
+        st.bestR = cand ? R : FLT_MAX;
+        st.bestIdx = cand ? j : 0;
+    } else if (V == st.M && cand && (R < st.bestR || (R == st.bestR && j < st.bestIdx))) {
+        st.bestR = R;
+        st.bestIdx = j;
+    }
+}
+__device__ __forceinline__ int loose_votes(const PairResult &h, bool upper) {
+    const float thr = 0.7f;   // votes that are possible within the margin: !(|r_k| - m > thr), NaN counts
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float rk = upper ? hi(h.r[k]) : lo(h.r[k]);
+        const float mk = upper ? hi(h.m) : lo(h.m);
+        v += int(!(fabsf(rk) - mk > thr));
+    }
+    return v;
+}
+
 // kVerified: FAST arithmetic is only a filter -- every hypothesis that could be the arg-min within the error
 // margin is re-evaluated in the EXACT arithmetic and all selection state is kept in exact values, so the
 // result equals the EXACT mode's (see the header comment of the verified path below).
 // kSplit: small-batch variant (one detection per CTA, warp w takes the rows r = w (mod kWarps) of every tile).
-template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, bool kVerified = false, bool kSplit = false>
+// kVMode: 0 = plain FAST search, 1 = VERIFIED with the all-six-votes filter (first pass; detections without a
+// six-vote plane are deferred), 2 = VERIFIED with the general filter (second pass: loose vote COUNT against
+// the warp's current exact max-votes; handles any max-votes, nothing is deferred).
+template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, int kVMode = 0, bool kSplit = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
+    constexpr bool kVerified = kVMode != 0;
+    constexpr bool kGeneral = kVMode == 2;
     constexpr int kTilePairs = kTile / 2;
     constexpr int kRowStep = kSplit ? kWarps : 1;
     constexpr uint32_t kPairBytes = 32;
@@ -428,6 +461,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
         int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
         bool six_seen = false;               // VERIFIED: some plane has six EXACT votes (warp-uniform)
+        int Mcur = -1;                       // VERIFIED general filter: exact max-votes so far (warp-uniform)
 
         for (int t = 0; t < n_tiles; ++t, ++it) {
             const int s = int(it % kStages);
@@ -469,7 +503,37 @@ GPP_UNROLL(GPP_M6_UNROLL)
                 const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                 PairResult h;
                 const int j = 2 * (base_pair + p);
-                if (kVerified) {
+                if (kGeneral) {
+                    // ---- general filter: a plane can only matter if, within its error margin, it may have more
+                    // votes than the warp's exact max-votes so far, or as many AND pass the z-check AND score no
+                    // worse than the warp's best exact residual at that vote count
+                    eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    const f2 R = resid_sum(h);
+                    const f2 Rlo = sub2(R, h.m);
+                    const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
+                    const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
+                    const bool trig0 = (V0 > Mcur) || (V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest));
+                    const bool trig1 = (V1 > Mcur) || (V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest));
+                    if (__any_sync(0xffffffffu, trig0 || trig1)) {
+                        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
+                        const unsigned below = (1u << lane) - 1u;
+                        if (q0) queue[qn + __popc(b0 & below)] = j;
+                        qn += __popc(b0);
+                        if (q1) queue[qn + __popc(b1 & below)] = j + 1;
+                        qn += __popc(b1);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            do {
+                                qn -= 32;
+                                verify_general(det, args.planes, queue[qn + lane], st);
+                            } while (qn >= 32);
+                            Mcur = __reduce_max_sync(0xffffffffu, st.M);
+                            wbest = __uint_as_float(__reduce_min_sync(
+                                0xffffffffu, __float_as_uint(st.M == Mcur ? st.bestR : FLT_MAX)));
+                        }
+                    }
+                } else if (kVerified) {
                     // ---- filter: a plane can only matter if, within its error margin, it has all six votes,
                     // passes the z-check and scores no worse than the warp's best exact residual so far
                     eval_pair_fast<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
@@ -524,7 +588,11 @@ GPP_UNROLL(GPP_M6_UNROLL)
             __syncwarp();
         }
 
-        if (kVerified) {
+        if (kGeneral) {
+            if (lane < qn) verify_general(det, args.planes, queue[lane], st);   // the last partial batch
+            qn = 0;
+            m6 = false;                              // the epilogue takes (max-votes, best) from `st`
+        } else if (kVerified) {
             bool saw6 = false;                       // the last partial batch of queued survivors
             if (lane < qn) saw6 = verify_one(det, args.planes, queue[lane], b6);
             qn = 0;
@@ -567,7 +635,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
             rbest = (lane < kWarps && Ml == Mw) ? buf[lane].r : FLT_MAX;
             idx = lane < kWarps ? buf[lane].idx : 0;
             rbest = warp_min_first(rbest, idx);
-            if (kVerified && Mw < 6) {               // no warp saw a six-vote plane: EXACT second pass
+            if (kVerified && !kGeneral && Mw < 6) {  // no warp saw a six-vote plane: second pass
                 if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
                 continue;
             }

@@ -214,8 +214,9 @@ class PlanePoller(object):
                                         _lib.ptr(votes), _lib.ptr(resid), _lib.ptr(zneg), _lib.ptr(margin))
         _lib.check(rc, 'gpp_debug_scores')
         if with_margin:
-            return votes, resid, zneg.astype(bool), margin
-        return votes, resid, zneg.astype(bool)
+            # + what the VERIFIED filters test: votes possible within the margin, z-check passable within it
+            return votes & 15, resid, (zneg & 1).astype(bool), margin, votes >> 4, (zneg & 2).astype(bool)
+        return votes & 15, resid, (zneg & 1).astype(bool)
 
     def debug_set_config(self, variant=0, ctas_per_sm=0):
         _lib.check(self._lib.gpp_debug_set_config(self._h, int(variant), int(ctas_per_sm)),

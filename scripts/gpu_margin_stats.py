@@ -14,7 +14,7 @@ for tag in ('22k', '10k', '1k'):
     loose_viol = 0
     for b in range(4):
         for d in range(100):
-            fv, fr, fz, fm = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=2, with_margin=True)
+            fv, fr, fz, fm, _, _ = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=2, with_margin=True)
             ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=0)
             rel = np.isfinite(er) & (ev == 6)
             if rel.any():

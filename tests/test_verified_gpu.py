@@ -84,13 +84,17 @@ def test_margin_bounds_the_fast_vs_exact_deviation(poller):
     worst = 0.0
     for b in range(3):
         for d in range(24):
-            fv, fr, fz, fm = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=2,
-                                                 with_margin=True)
-            ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=0)
-            rel = np.isfinite(er) & (er < 6 * 0.7 + 1.0)            # anything that can carry six votes
-            assert np.isfinite(fm[rel]).all() and (fm[rel] > 0).all()
-            ratio = np.abs(fr[rel] - er[rel]) / fm[rel]
-            worst = max(worst, float(ratio.max()) if ratio.size else 0.0)
+            for which in (1, 2):
+                fv, fr, fz, fm, vhi, zok = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b],
+                                                               which=which, with_margin=True)
+                ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=0)
+                rel = np.isfinite(er) & (er < 6 * 0.7 + 1.0)        # anything that can carry six votes
+                assert np.isfinite(fm[rel]).all() and (fm[rel] > 0).all()
+                ratio = np.abs(fr[rel] - er[rel]) / fm[rel]
+                worst = max(worst, float(ratio.max()) if ratio.size else 0.0)
+                # superset properties the filters rely on, on EVERY hypothesis
+                assert (vhi >= ev).all()                            # votes possible within the margin >= exact votes
+                assert zok[~ez].all()                               # exact z-check passes -> filter lets it pass
     assert worst < 0.25, worst
 
 
