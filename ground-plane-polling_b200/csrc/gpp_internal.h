@@ -69,7 +69,6 @@ struct gpp_handle {
     int occ2[3] = {0, 0, 0};                     // fast kernel: [register-budget variant]
     int occ3[2] = {0, 0};                        // verified kernel: [register-budget variant]
     int occ_split[4] = {0, 0, 0, 0};             // small-batch (one detection per CTA) kernels: exact, fast, verified, f64
-    int occ_general[2] = {0, 0};                 // verified second pass (general filter): batch, split
     int force_split = 0;                         // tuning hook: > 0 force the small-batch kernels, < 0 forbid them
 };
 

@@ -132,8 +132,6 @@ constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * s
 #define GPP_K_EXACT_SPLIT poll_kernel<ExactF32, kWarps, 1, kTile32, kStages, true>
 #define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 0, true>
 #define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 1, true>
-#define GPP_K_GENERAL poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 2, false>
-#define GPP_K_GENERAL_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 2, true>
 constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
                           2 * kWarps * sizeof(WarpPartial<float>);
 
@@ -166,8 +164,6 @@ int configure_kernels(gpp_handle *h) {
     if ((rc = configure_kernel(GPP_K_FAST_SPLIT, kSmem2, &h->occ_split[1]))) return rc;
     if ((rc = configure_kernel(GPP_K_VERIFIED_SPLIT, kSmem2, &h->occ_split[2]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64_SPLIT, kSmem64, &h->occ_split[3]))) return rc;
-    if ((rc = configure_kernel(GPP_K_GENERAL, kSmem2, &h->occ_general[0]))) return rc;
-    if ((rc = configure_kernel(GPP_K_GENERAL_SPLIT, kSmem2, &h->occ_general[1]))) return rc;
     return GPP_OK;
 }
 
@@ -311,27 +307,17 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
         b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
         b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
-        b.defer_list = nullptr; b.defer_count = nullptr;
         b.det_list = a.det_list; b.det_count = a.det_count;
         const bool split = use_split(h, a.n_det);
         const long long n_groups = split ? a.n_det : (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
             if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
-            b.defer_list = w->list; b.defer_count = w->count;
-            // second pass: the deferred detections (max-votes < 6) through the general filter; the count is
-            // read on the device, the grid is sized for the worst case
-            PollArgs2<float> c = b;
-            c.det_list = w->list; c.det_count = w->count;
-            c.defer_list = nullptr; c.defer_count = nullptr;
             if (split) {
                 GPP_K_VERIFIED_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[2]), kWarps * 32, kSmem2, s>>>(b);
-                GPP_K_GENERAL_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_general[1]), kWarps * 32, kSmem2, s>>>(c);
             } else {
                 verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
-                GPP_K_GENERAL<<<(unsigned)grid_for(h, n_groups, h->occ_general[0]), kWarps * 32, kSmem2, s>>>(c);
             }
-            h->launches += 1;
         } else if (split) {
             GPP_K_FAST_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[1]), kWarps * 32, kSmem2, s>>>(b);
         } else {

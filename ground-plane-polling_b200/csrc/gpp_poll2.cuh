@@ -317,10 +317,6 @@ struct PollArgs2 {
     long long n_det;
     T *keypoints, *keyplanes, *residuals;
     long long *best;
-    // VERIFIED mode: detections whose max-votes is not known to be 6 after the first tile are handed to a
-    // second pass (scalar EXACT kernel over this work list) instead of slowing their CTA down
-    long long *defer_list;
-    unsigned int *defer_count;
     // optional work list: process det_list[0 .. *det_count) instead of 0 .. n_det (rows that repeat the
     // previous row of their image -- FilterDetections' -1 padding -- are computed once and copied)
     const long long *det_list;
@@ -337,19 +333,8 @@ __device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n
 
 constexpr int kVerifyQueue = 96;
 
-// VERIFIED: exact re-evaluation of one queued plane; the lane keeps the lexicographic minimum (residual, index)
-__device__ __forceinline__ bool verify_one(const Detection<ExactF32> &de, const float4 *__restrict__ planes, int j,
-                                           LaneBest &b) {
-    const float4 pl = planes[j];
-    int V; float R; bool z;
-    exact_one(de, pl.x, pl.y, pl.z, pl.w, V, R, z);
-    const bool better = (V == 6) && !z && (R < b.bestR || (R == b.bestR && j < b.bestIdx));
-    b.bestR = better ? R : b.bestR;
-    b.bestIdx = better ? j : b.bestIdx;
-    return V == 6;                               // max-votes == 6 is established (z-check or not)
-}
-
-// VERIFIED, general filter: exact re-evaluation with the full (max-votes, residual, index) bookkeeping
+// VERIFIED: exact re-evaluation of one queued plane with the full (max-votes, residual, index) bookkeeping;
+// ties break by index explicitly (the queue is not drained in index order)
 __device__ __forceinline__ void verify_general(const Detection<ExactF32> &de, const float4 *__restrict__ planes, int j,
                                                LaneState<float> &st) {
     const float4 pl = planes[j];
@@ -381,13 +366,12 @@ __device__ __forceinline__ int loose_votes(const PairResult &h, bool upper) {
 // margin is re-evaluated in the EXACT arithmetic and all selection state is kept in exact values, so the
 // result equals the EXACT mode's (see the header comment of the verified path below).
 // kSplit: small-batch variant (one detection per CTA, warp w takes the rows r = w (mod kWarps) of every tile).
-// kVMode: 0 = plain FAST search, 1 = VERIFIED with the all-six-votes filter (first pass; detections without a
-// six-vote plane are deferred), 2 = VERIFIED with the general filter (second pass: loose vote COUNT against
-// the warp's current exact max-votes; handles any max-votes, nothing is deferred).
+// kVMode: 0 = plain FAST search, 1 = VERIFIED.  The verified filter has two warp-uniform phases: while the
+// warp's exact max-votes is below 6 it counts the votes that are possible within the margin (general phase);
+// once a plane with six exact votes is known it tests max_k |r_k| - m <= 0.7 (all-six-votes phase).
 template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, int kVMode = 0, bool kSplit = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
     constexpr bool kVerified = kVMode != 0;
-    constexpr bool kGeneral = kVMode == 2;
     constexpr int kTilePairs = kTile / 2;
     constexpr int kRowStep = kSplit ? kWarps : 1;
     constexpr uint32_t kPairBytes = 32;
@@ -460,8 +444,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         bool m6 = false;
         float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
         int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
-        bool six_seen = false;               // VERIFIED: some plane has six EXACT votes (warp-uniform)
-        int Mcur = -1;                       // VERIFIED general filter: exact max-votes so far (warp-uniform)
+        int Mcur = -1;                       // VERIFIED: exact max-votes so far in this warp (warp-uniform)
 
         for (int t = 0; t < n_tiles; ++t, ++it) {
             const int s = int(it % kStages);
@@ -503,68 +486,58 @@ GPP_UNROLL(GPP_M6_UNROLL)
                 const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
                 PairResult h;
                 const int j = 2 * (base_pair + p);
-                if (kGeneral) {
-                    // ---- general filter: a plane can only matter if, within its error margin, it may have more
-                    // votes than the warp's exact max-votes so far, or as many AND pass the z-check AND score no
-                    // worse than the warp's best exact residual at that vote count
-                    eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                    const f2 R = resid_sum(h);
-                    const f2 Rlo = sub2(R, h.m);
-                    const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
-                    const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
-                    const bool trig0 = (V0 > Mcur) || (V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest));
-                    const bool trig1 = (V1 > Mcur) || (V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest));
-                    if (__any_sync(0xffffffffu, trig0 || trig1)) {
-                        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
-                        const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
+                if (kVerified) {
+                    // ---- filter.  A plane survives iff, within its error margin m, it could matter:
+                    //   all-six phase (Mcur == 6): it has six votes, passes the z-check and scores no worse than
+                    //                              the warp's best exact residual so far;
+                    //   general phase (Mcur < 6):  it may have MORE votes than the exact max-votes so far, or as
+                    //                              many and pass the z-check and score no worse than the best.
+                    // Comparisons are written so that NaN (degenerate fast arithmetic) always survives.
+                    bool trig0, trig1, urgent = false;
+                    if (Mcur == 6) {
+                        eval_pair_fast<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        const f2 R = resid_sum(h);
+                        const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                                         rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+                        const f2 rlo = sub2(rm, h.m);                   // lower bounds (margin subtracted)
+                        const f2 Rlo = sub2(R, h.m);
+                        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);      // upper bound of z_dir_check
+                        trig0 = !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
+                        trig1 = !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+                    } else {
+                        eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        const f2 R = resid_sum(h);
+                        const f2 Rlo = sub2(R, h.m);
+                        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
+                        const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
+                        trig0 = (V0 > Mcur) || (V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest));
+                        trig1 = (V1 > Mcur) || (V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest));
+                        urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
+                    }
+                    const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
+                    const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
+                    if (b0 | b1) {
+                        // ---- queue the survivors; the whole warp re-evaluates them 32 at a time (exact)
                         const unsigned below = (1u << lane) - 1u;
                         if (q0) queue[qn + __popc(b0 & below)] = j;
                         qn += __popc(b0);
                         if (q1) queue[qn + __popc(b1 & below)] = j + 1;
                         qn += __popc(b1);
                         __syncwarp();
-                        if (qn >= 32) {
-                            do {
+                        const bool flush_all = __any_sync(0xffffffffu, urgent);
+                        if (qn >= 32 || flush_all) {
+                            while (qn >= 32) {
                                 qn -= 32;
                                 verify_general(det, args.planes, queue[qn + lane], st);
-                            } while (qn >= 32);
+                            }
+                            if (flush_all && qn > 0) {
+                                if (lane < qn) verify_general(det, args.planes, queue[lane], st);
+                                qn = 0;
+                            }
+                            __syncwarp();
                             Mcur = __reduce_max_sync(0xffffffffu, st.M);
                             wbest = __uint_as_float(__reduce_min_sync(
                                 0xffffffffu, __float_as_uint(st.M == Mcur ? st.bestR : FLT_MAX)));
-                        }
-                    }
-                } else if (kVerified) {
-                    // ---- filter: a plane can only matter if, within its error margin, it has all six votes,
-                    // passes the z-check and scores no worse than the warp's best exact residual so far
-                    eval_pair_fast<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                    const f2 R = resid_sum(h);
-                    const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                                     rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
-                    const f2 rlo = sub2(rm, h.m);                       // lower bounds (margin subtracted)
-                    const f2 Rlo = sub2(R, h.m);
-                    const f2 zhi = fma2(h.m, bc(16.0f), h.zc);          // upper bound of z_dir_check
-                    // comparisons written so that NaN (degenerate fast arithmetic) always triggers; until an exact
-                    // six-vote plane is known (max-votes == 6 established) every possible six-vote plane survives
-                    const bool trig0 = !(lo(rlo) > 0.7f) && (!six_seen || (!(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest)));
-                    const bool trig1 = !(hi(rlo) > 0.7f) && (!six_seen || (!(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest)));
-                    if (__any_sync(0xffffffffu, trig0 || trig1)) {
-                        // ---- queue the survivors; they are re-evaluated 32 at a time by the whole warp
-                        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
-                        const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
-                        const unsigned below = (1u << lane) - 1u;
-                        if (q0) queue[qn + __popc(b0 & below)] = j;
-                        qn += __popc(b0);
-                        if (q1) queue[qn + __popc(b1 & below)] = j + 1;
-                        qn += __popc(b1);
-                        __syncwarp();
-                        if (qn >= 32) {
-                            bool saw6 = false;
-                            do {
-                                qn -= 32;
-                                saw6 |= verify_one(det, args.planes, queue[qn + lane], b6);
-                            } while (qn >= 32);
-                            six_seen = six_seen || __any_sync(0xffffffffu, saw6);
-                            wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
                         }
                     }
                 } else {
@@ -588,27 +561,11 @@ GPP_UNROLL(GPP_M6_UNROLL)
             __syncwarp();
         }
 
-        if (kGeneral) {
+        if (kVerified) {
             if (lane < qn) verify_general(det, args.planes, queue[lane], st);   // the last partial batch
             qn = 0;
+            __syncwarp();
             m6 = false;                              // the epilogue takes (max-votes, best) from `st`
-        } else if (kVerified) {
-            bool saw6 = false;                       // the last partial batch of queued survivors
-            if (lane < qn) saw6 = verify_one(det, args.planes, queue[lane], b6);
-            qn = 0;
-            six_seen = six_seen || __any_sync(0xffffffffu, saw6);
-            if (!kSplit) {
-                if (!six_seen) {
-                    // no plane has six exact votes: max-votes < 6, the all-six-votes filter does not apply ->
-                    // this detection goes to the EXACT second pass (warp-uniform decision)
-                    if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
-                    continue;
-                }
-                m6 = true;
-            } else {
-                m6 = six_seen;                       // this warp's share; merged below
-                if (!m6) st.reset(FLT_MAX);          // contributes M = -1, no candidate
-            }
         }
         // ---- epilogue: warp reduction, lazy first-masked search, exact recompute of the winner
         int Mw;
@@ -635,10 +592,6 @@ GPP_UNROLL(GPP_M6_UNROLL)
             rbest = (lane < kWarps && Ml == Mw) ? buf[lane].r : FLT_MAX;
             idx = lane < kWarps ? buf[lane].idx : 0;
             rbest = warp_min_first(rbest, idx);
-            if (kVerified && !kGeneral && Mw < 6) {  // no warp saw a six-vote plane: second pass
-                if (lane == 0 && m < args.n_det) args.defer_list[atomicAdd(args.defer_count, 1u)] = m;
-                continue;
-            }
         }
         const bool have_cand = rbest < FLT_MAX;
         bool sentinel = false;
