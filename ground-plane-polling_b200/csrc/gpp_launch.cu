@@ -118,7 +118,8 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
 }
 
 constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t) +
-                          sizeof(int) * kWarps * kVerifyQueue + 2 * kWarps * sizeof(WarpPartial<float>);
+                          sizeof(int) * kWarps * kVerifyQueue + 2 * kWarps * sizeof(WarpPartial<float>) +
+                          2 * sizeof(unsigned int);
 constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t) +
                            2 * kWarps * sizeof(WarpPartial<double>);
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
@@ -177,7 +178,7 @@ static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_
     gpp_handle::WorkSlot &w = h->work[h->next_work++ % gpp_handle::kWorkSlots];
     cudaError_t e = cudaSuccess;
     if (!w.done) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
-    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, 4 * sizeof(unsigned int));
     if (e == cudaSuccess && w.used) e = cudaStreamWaitEvent(s, w.done, 0);   // previous user of this slot
     if (e == cudaSuccess && n_det > w.cap) {
         // cudaMalloc/cudaFree are not stream-ordered: the previous user must be finished on the host side too
@@ -188,7 +189,7 @@ static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_
         if (e == cudaSuccess) e = cudaMalloc(&w.unique, (size_t)n_det);
         if (e == cudaSuccess) w.cap = n_det;
     }
-    if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, 2 * sizeof(unsigned int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, 4 * sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "work list setup: %s", cudaGetErrorString(e));
     *out = &w;
     return GPP_OK;
@@ -308,6 +309,7 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
         b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
         b.det_list = a.det_list; b.det_count = a.det_count;
+        b.group_counter = w->count + 2;
         const bool split = use_split(h, a.n_det);
         const long long n_groups = split ? a.n_det : (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {

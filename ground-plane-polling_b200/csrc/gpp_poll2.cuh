@@ -321,6 +321,9 @@ struct PollArgs2 {
     // previous row of their image -- FilterDetections' -1 padding -- are computed once and copied)
     const long long *det_list;
     const unsigned int *det_count;
+    // dynamic scheduling: detection groups are claimed from this device counter (zeroed before the launch), so
+    // CTAs that drew cheap detections take more groups instead of idling at the end of the kernel
+    unsigned int *group_counter;
 };
 
 // kTile planes per smem tile (multiple of 64), one detection per warp.
@@ -391,8 +394,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     const int n_tiles = (NP + kTilePairs - 1) / kTilePairs;
     const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
     const long long n_groups = kSplit ? n_work : (n_work + kWarps - 1) / kWarps;
-    const long long my_groups = (n_groups > blockIdx.x) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_tiles = my_groups * n_tiles;
+    unsigned int *claim = reinterpret_cast<unsigned int *>(partial + 2 * kWarps);       // [2]: groups k, k+1
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -401,6 +403,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
             mbar_init(&empty_bar[s], kWarps);
         }
         mbar_fence_init();
+        claim[0] = atomicAdd(args.group_counter, 1u);
+        claim[1] = atomicAdd(args.group_counter, 1u);
     }
     __syncthreads();
 
@@ -414,13 +418,28 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     reinterpret_cast<const unsigned char *>(args.pairs) + size_t(t) * kTilePairs * kPairBytes, bytes,
                     &full_bar[s]);
     };
-    if (threadIdx.x == 0) {
-        const long long pre = total_tiles < kStages ? total_tiles : kStages;
-        for (long long it = 0; it < pre; ++it) issue(it);
-    }
+    // producer state (thread 0 only): tiles issued so far / tiles known to be needed (groups claimed so far)
+    long long issued = 0, known_tiles = 0;
+    auto pump = [&](long long max_index) {
+        while (issued < known_tiles && issued <= max_index) {
+            if (issued >= kStages)                                   // the slot's previous tile must be released
+                mbar_wait(&empty_bar[issued % kStages], uint32_t(((issued / kStages) - 1) & 1));
+            issue(issued);
+            ++issued;
+        }
+    };
 
     long long it = 0;
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    for (long long k = 0;; ++k) {
+        const unsigned int g32 = claim[k & 1], g_next = claim[(k + 1) & 1];
+        if (g32 >= n_groups) break;                                  // CTA-uniform
+        __syncthreads();                                             // everyone has read claim[k & 1]
+        if (threadIdx.x == 0) {
+            claim[k & 1] = atomicAdd(args.group_counter, 1u);        // group k + 2
+            known_tiles = (k + 1 + (g_next < n_groups ? 1 : 0)) * n_tiles;
+            pump(it - 1 + kStages);
+        }
+        const long long g = g32;
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
         const long long w_id = kSplit ? g : g * kWarps + warp;
         long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
@@ -551,13 +570,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (threadIdx.x == 0 && it >= 1) {
-                const long long prev = it - 1;
-                if (prev + kStages < total_tiles) {
-                    mbar_wait(&empty_bar[prev % kStages], uint32_t((prev / kStages) & 1));
-                    issue(prev + kStages);
-                }
-            }
+            if (threadIdx.x == 0) pump(it - 1 + kStages);      // skewed by one tile: rarely waits for the slowest warp
             __syncwarp();
         }
 
@@ -583,7 +596,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
         rbest = warp_min_first(rbest, idx);
         if (kSplit) {
             // merge the warps' partial results (double-buffered by group parity: one barrier per group)
-            WarpPartial<float> *buf = partial + ((g / gridDim.x) & 1) * kWarps;
+            WarpPartial<float> *buf = partial + (k & 1) * kWarps;
             if (lane == 0) { buf[warp].r = rbest; buf[warp].M = Mw; buf[warp].idx = idx; }
             __syncthreads();
             if (warp != 0) continue;
