@@ -140,6 +140,8 @@ struct PairResult {
     f2 r[6];           // signed residuals dist_k - target_k (abs is applied by the consumers)
     f2 zc;             // z_dir_check
     f2 m;              // VERIFIED mode: bound on |fast - exact| of the residual sum (see eval_pair_fast)
+    f2 za0, za2, zb0, zb2;   // lazy z_dir_check: the x/z components of X_l - X_m and X_r - X_m
+    __device__ __forceinline__ void finish_zc() { zc = fma2(za2, zb0, neg2(mul2(za0, zb2))); }
 };
 
 // Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
@@ -210,7 +212,7 @@ __device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f
 //   X_t = X_m - q n,  |X_m - X_t| = |q|
 //   |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
 // 60 FMA-pipe results, 9 MUFU and ~11 ALU-pipe instructions per hypothesis (the direct formulation: 92 / 10).
-template <bool kMergedRcp, bool kMargin>
+template <bool kMergedRcp, bool kMargin, bool kLazyZ = false>
 __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
     const f2 t0 = dot3p(n0, n1, n2, D.dl[0], D.dl[1], D.dl[2], false);
     const f2 t1 = dot3p(n0, n1, n2, D.dm[0], D.dm[1], D.dm[2], false);
@@ -252,7 +254,11 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
         b[i] = fma2(bc(D.dr[i]), s2, nxm);               // X_r - X_m
         c[i] = sub2(a[i], b[i]);                         // X_l - X_r
     }
-    out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
+    if (kLazyZ) {           // z_dir_check is only formed for the few pairs that get that far (see the callers)
+        out.za0 = a[0]; out.za2 = a[2]; out.zb0 = b[0]; out.zb2 = b[2];
+    } else {
+        out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
+    }
     const f2 num = fma2(mul2(u, s1), bc(-D.G), mul2(cs1, bc(D.T)));
     const f2 q = mul2(num, iden);
 #define GPP_SQN(v) fma2(v[2], v[2], fma2(v[1], v[1], mul2(v[0], v[0])))
@@ -497,6 +503,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
                     // candidates found under a lower running max are masked from now on
                     b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
                     b6.bestIdx = st.bestIdx;
+                    wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
                 }
             }
 GPP_UNROLL(GPP_M6_UNROLL)
@@ -514,15 +521,23 @@ GPP_UNROLL(GPP_M6_UNROLL)
                     // Comparisons are written so that NaN (degenerate fast arithmetic) always survives.
                     bool trig0, trig1, urgent = false;
                     if (Mcur == 6) {
-                        eval_pair_fast<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                        const f2 R = resid_sum(h);
-                        const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                                         rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
-                        const f2 rlo = sub2(rm, h.m);                   // lower bounds (margin subtracted)
-                        const f2 Rlo = sub2(R, h.m);
-                        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);      // upper bound of z_dir_check
-                        trig0 = !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
-                        trig1 = !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+                        // the residual test comes first: once the warp's best is good, almost no pair passes it,
+                        // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp
+                        eval_pair_fast<true, true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        const f2 Rlo = sub2(resid_sum(h), h.m);         // lower bound of the residual sum
+                        trig0 = !(lo(Rlo) > wbest);
+                        trig1 = !(hi(Rlo) > wbest);
+                        if (__any_sync(0xffffffffu, trig0 || trig1)) {
+                            h.finish_zc();
+                            const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                                             rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+                            const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
+                            const f2 zhi = fma2(h.m, bc(16.0f), h.zc);  // upper bound of z_dir_check
+                            trig0 = trig0 && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
+                            trig1 = trig1 && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
+                        } else {
+                            trig0 = trig1 = false;
+                        }
                     } else {
                         eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
@@ -560,12 +575,17 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         }
                     }
                 } else {
-                    eval_pair<true>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    eval_pair_fast<true, false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                     const f2 R = resid_sum(h);
-                    b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                               lo(h.zc), lo(R), j);
-                    b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
-                               hi(h.zc), hi(R), j + 1);
+                    // only a pair that scores no worse than the warp's best so far can change the result
+                    if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
+                        h.finish_zc();
+                        b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                                   lo(h.zc), lo(R), j);
+                        b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
+                                   hi(h.zc), hi(R), j + 1);
+                        wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+                    }
                 }
             }
             __syncwarp();
