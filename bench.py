@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 
 W_ALG = 148.0                      # algorithmic FLOP per hypothesis, SURVEY.md section 8.4
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-KERNEL_OF_MODE = {'verified': 'gpp::poll2_kernel<PackFast, verified> (+ gpp::poll_kernel<ExactF32> second pass, both timed)',
+KERNEL_OF_MODE = {'verified': 'gpp::poll2_kernel<PackFast, verified>',
                   'fast': 'gpp::poll2_kernel<PackFast>', 'exact': 'gpp::poll_kernel<ExactF32>'}
 METRIC = 'ground-plane hypotheses/sec (dets x planes)'
 UNIT = 'hypotheses/s'
@@ -334,6 +334,13 @@ def main():
                'c_port_sample': '%d images (%.1f s), fused C restatement, all host threads' % (c_img, c_dt),
                'host_cpu_count': os.cpu_count()}
 
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'r01f_traffic_c4.json')
+    if args.mode == 'verified' and args.images == 4096 and args.planes == '22k' and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # bytes per launch, from the ncu capture
+        traffic_src = 'profiles/r01f_traffic_c4.json (ncu --set full capture of this launch)'
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         achieved = W_ALG * value / world / 1e12              # per-GPU TFLOP/s of algorithmic work
@@ -348,7 +355,8 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak_tflops, 'traffic': None,
+                         'frac': achieved / peak_tflops, 'traffic': traffic, 'traffic_unit': 'bytes/launch',
+                         'traffic_source': traffic_src,
                          'peak_source': 'libgpp FFMA microbenchmark, same run (MEASURED_PEAKS.json has no FP32 entry)',
                          'nominal_peak': NOMINAL_FP32_TFLOPS, 'frac_of_nominal': achieved / NOMINAL_FP32_TFLOPS,
                          'flop_per_hypothesis': W_ALG, 'kernel': KERNEL_OF_MODE[args.mode],
