@@ -249,6 +249,11 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
         for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
         D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
         D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
+        const float d0 = det.dl[0] * det.dl[0] + det.dl[1] * det.dl[1] + det.dl[2] * det.dl[2];
+        const float d1 = det.dm[0] * det.dm[0] + det.dm[1] * det.dm[1] + det.dm[2] * det.dm[2];
+        const float d2 = det.dr[0] * det.dr[0] + det.dr[1] * det.dr[1] + det.dr[2] * det.dr[2];
+        D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
+        D.msT = D.ms * D.T;
     }
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.pairs);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
@@ -260,7 +265,7 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
         const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
         // votes: fast count + 16 x the count that is possible within the margin (the VERIFIED filters' test);
         // zneg: fast z-check + 2 x "may pass the z-check within the margin"
-        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
+        const f2 zhi = z_upper(h, D);
         votes[2 * p] = V0 + 16 * loose_votes(h, false); resid[2 * p] = lo(R);
         zneg[2 * p] = (lo(h.zc) < 0.0f ? 1 : 0) + (!(lo(zhi) < 0.0f) ? 2 : 0);
         if (margin) margin[2 * p] = lo(h.m);

@@ -134,6 +134,7 @@ struct DetConst {
     float td[6];
     float T;           // |d_t|^2  (fast formulation only)
     float G;           // d_t . d_m (fast formulation only)
+    float ms, msT;     // VERIFIED: K 2^-24 max_k |d_k|^2 and the same times T (margin scales, ray-scale invariant)
 };
 
 struct PairResult {
@@ -145,9 +146,9 @@ struct PairResult {
 };
 
 // Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
-// score mainly through the rounding of t_k = n.d_k (absolute ~u) divided by |t_k|: a point at distance
-// |X_k| = |d_k| |d| / |t_k| moves by ~ u |X_k| / |t_k|, i.e. ~ u |d| i_max^2 with i_k = 1/|t_k| (quadratic in
-// depth), and X_t additionally by ~1/(perp.n).  kMarginK is that first-order scale times a safety factor; the
+// score mainly through the rounding of t_k = n.d_k (absolute ~u |d_k|) divided by |t_k|: a point at distance
+// |X_k| = |d_k| |d| / |t_k| moves by ~ u |d_k| |X_k| / |t_k| = u |d| (|d_k| i_k)^2 with i_k = 1/|t_k| (quadratic
+// in depth, invariant under a rescaling of the rays), and X_t additionally by ~1/(perp.n).  kMarginK is that first-order scale times a safety factor; the
 // VERIFIED mode is validated against the EXACT mode on full benchmark batches (tests/test_verified_gpu.py).
 #ifndef GPP_MARGIN_K
 #define GPP_MARGIN_K 64.0f
@@ -240,7 +241,7 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
     if (kMargin) {
         const f2 imax = pk(max3f(fabsf(lo(i0)), fabsf(lo(i1)), lo(i2)), max3f(fabsf(hi(i0)), fabsf(hi(i1)), hi(i2)));
         const f2 w = mul2(mul2(imax, imax), ad);                         // |d| / t_min^2
-        out.m = mul2(w, fma2(abs2(iden), bc(kMarginScale * D.T), bc(kMarginScale)));   // K u w (1 + T/|perp.n|)
+        out.m = mul2(w, fma2(abs2(iden), bc(D.msT), bc(D.ms)));          // K u |d_k|^2 w (1 + T/|perp.n|)
     }
     // n.X_k = |d| sign(t_k): sign transfer on the ALU pipe
     const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
@@ -359,6 +360,12 @@ __device__ __forceinline__ void verify_general(const Detection<ExactF32> &de, co
         st.bestIdx = j;
     }
 }
+// upper bound of z_dir_check = (a x b).y with a = X_l - X_m, b = X_r - X_m: the positions move by <= m, so the
+// cross product moves by <= m (|a| + |b|) (+ m^2); |a| = r[1] + target_1, |b| = r[2] + target_2
+__device__ __forceinline__ f2 z_upper(const PairResult &h, const DetConst &D) {
+    const f2 len = add2(add2(abs2(add2(h.r[1], bc(D.td[1]))), abs2(add2(h.r[2], bc(D.td[2])))), h.m);
+    return fma2(h.m, fma2(len, bc(4.0f), bc(1.0f)), h.zc);
+}
 __device__ __forceinline__ int loose_votes(const PairResult &h, bool upper) {
     const float thr = 0.7f;   // votes that are possible within the margin: !(|r_k| - m > thr), NaN counts
     int v = 0;
@@ -461,6 +468,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
         D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
         D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
+        {
+            const float d0 = det.dl[0] * det.dl[0] + det.dl[1] * det.dl[1] + det.dl[2] * det.dl[2];
+            const float d1 = det.dm[0] * det.dm[0] + det.dm[1] * det.dm[1] + det.dm[2] * det.dm[2];
+            const float d2 = det.dr[0] * det.dr[0] + det.dr[1] * det.dr[1] + det.dr[2] * det.dr[2];
+            D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
+            D.msT = D.ms * D.T;
+        }
 
         LaneState<float> st;                 // general mode (max votes not yet known to be 6)
         st.reset(FLT_MAX);
@@ -532,7 +546,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                             const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
                                              rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
                             const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
-                            const f2 zhi = fma2(h.m, bc(16.0f), h.zc);  // upper bound of z_dir_check
+                            const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
                             trig0 = trig0 && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
                             trig1 = trig1 && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
                         } else {
@@ -542,7 +556,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
                         const f2 Rlo = sub2(R, h.m);
-                        const f2 zhi = fma2(h.m, bc(16.0f), h.zc);
+                        const f2 zhi = z_upper(h, D);
                         const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
                         trig0 = (V0 > Mcur) || (V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest));
                         trig1 = (V1 > Mcur) || (V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest));

@@ -137,3 +137,30 @@ def test_small_batch_split_kernels_equal_oracle(gpp, poller, force):
     assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
     valid = orient >= 0          # padding rows are degenerate (all key-points equal): pure rounding-noise ties
     assert np.mean(fast[3][valid] == want[3][valid]) > 0.97
+
+
+@pytest.mark.parametrize('ray_scale', [1.0, 1000.0, 1e-3])
+def test_verified_is_robust_to_ray_scale_and_odd_geometry(gpp, poller, ray_scale):
+    """The margin must not depend on how P_inv happens to be scaled (rays are only defined up to a factor), and
+    the z-check bound must hold for any geometry: tiny / huge dimensions, far-away and very close objects."""
+    planes = load_planes('10k')[:4000]
+    boxes, dims, orient, P_inv = synthetic.synth_detections(2, 60, planes, seed=505)
+    dims = dims.copy()
+    dims[0, :10] *= 12.0                     # absurdly large boxes: key-point distances of tens of metres
+    dims[0, 10:20] *= 0.05                   # absurdly small ones
+    boxes = boxes.copy()
+    boxes[1, :10, 4:] = boxes[1, :10, 4:] * 0.02 + 650.0      # key-points a few pixels apart: very distant geometry
+    P_scaled = P_inv * ray_scale
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_scaled, planes, return_index=True)
+    got = gpp.fit_road_planes(boxes, dims, orient, P_scaled, planes, mode='verified', return_index=True)
+    _same(got, want)
+    poller.set_planes(planes)
+    for b, d in ((0, 0), (0, 5), (0, 12), (1, 3), (1, 30), (0, 40)):
+        for which in (1, 2):
+            fv, fr, fz, fm, vhi, zok = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_scaled[b],
+                                                           which=which, with_margin=True)
+            ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_scaled[b], which=0)
+            assert (vhi >= ev).all()
+            assert zok[~ez].all()
+            fin = np.isfinite(er) & np.isfinite(fr)
+            assert (np.abs(fr[fin] - er[fin]) <= fm[fin]).all()
