@@ -38,9 +38,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (complete_tx)
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (complete_tx).
+// The slot being overwritten was last READ through the generic proxy by the consumer warps; their release is
+// observed by the producer through the empty mbarrier, and the proxy fence orders those generic-proxy
+// accesses before this async-proxy write.
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
                                             uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             smem_u32(smem_dst)),
