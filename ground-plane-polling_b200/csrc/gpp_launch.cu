@@ -119,7 +119,7 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
 
 constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t) +
                           sizeof(int) * kWarps * kVerifyQueue + 2 * kWarps * sizeof(WarpPartial<float>) +
-                          2 * sizeof(unsigned int);
+                          2 * sizeof(unsigned int) + sizeof(float) * 20 * kWarps;
 constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t) +
                            2 * kWarps * sizeof(WarpPartial<double>);
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
@@ -245,15 +245,8 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
     {
         Detection<ExactF32> det;
         load_detection<ExactF32, ExactF32>(det, a.boxes, a.dims, a.orient[0], a.pinv);
-        for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
         for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
-        D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
-        D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
-        const float d0 = det.dl[0] * det.dl[0] + det.dl[1] * det.dl[1] + det.dl[2] * det.dl[2];
-        const float d1 = det.dm[0] * det.dm[0] + det.dm[1] * det.dm[1] + det.dm[2] * det.dm[2];
-        const float d2 = det.dr[0] * det.dr[0] + det.dr[1] * det.dr[1] + det.dr[2] * det.dr[2];
-        D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
-        D.msT = D.ms * D.T;
+        fast_constants(D, det);
     }
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.pairs);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
@@ -261,6 +254,7 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
         PairResult h;
         eval_pair_fast<kSix, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
         const f2 R = resid_sum(h);
+        finalize_margin(h, R, D);
         const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
         const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
         // votes: fast count + 16 x the count that is possible within the margin (the VERIFIED filters' test);

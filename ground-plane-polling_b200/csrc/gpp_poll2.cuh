@@ -105,17 +105,6 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {      // NaN-
 }
 
 // ------------------------------------------------------------------ packed policies
-struct PackExact {
-    static constexpr bool kExact = true;
-    typedef ExactF32 Scalar;
-    // a*b + c, a*b - c with two roundings (the canonical, FMA-free arithmetic)
-    static __device__ __forceinline__ f2 madd(f2 a, f2 b, f2 c) { return add2(mul2(a, b), c); }
-    static __device__ __forceinline__ f2 div(f2 a, f2 b) {
-        return pk(__fdiv_rn(lo(a), lo(b)), __fdiv_rn(hi(a), hi(b)));
-    }
-    static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(__fsqrt_rn(lo(a)), __fsqrt_rn(hi(a))); }
-};
-
 struct PackFast {
     static constexpr bool kExact = false;
     typedef FastF32 Scalar;
@@ -128,23 +117,6 @@ struct PackFast {
 #endif
 };
 
-// per-detection constants of the packed kernels (warp-uniform scalars)
-struct DetConst {
-    float dl[3], dm[3], dr[3], dt[3];
-    float td[6];
-    float T;           // |d_t|^2  (fast formulation only)
-    float G;           // d_t . d_m (fast formulation only)
-    float ms, msT;     // VERIFIED: K 2^-24 max_k |d_k|^2 and the same times T (margin scales, ray-scale invariant)
-};
-
-struct PairResult {
-    f2 r[6];           // signed residuals dist_k - target_k (abs is applied by the consumers)
-    f2 zc;             // z_dir_check
-    f2 m;              // VERIFIED mode: bound on |fast - exact| of the residual sum (see eval_pair_fast)
-    f2 za0, za2, zb0, zb2;   // lazy z_dir_check: the x/z components of X_l - X_m and X_r - X_m
-    __device__ __forceinline__ void finish_zc() { zc = fma2(za2, zb0, neg2(mul2(za0, zb2))); }
-};
-
 // Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
 // score mainly through the rounding of t_k = n.d_k (absolute ~u |d_k|) divided by |t_k|: a point at distance
 // |X_k| = |d_k| |d| / |t_k| moves by ~ u |d_k| |X_k| / |t_k| = u |d| (|d_k| i_k)^2 with i_k = 1/|t_k| (quadratic
@@ -155,77 +127,80 @@ struct PairResult {
 #endif
 constexpr float kMarginScale = GPP_MARGIN_K * 5.9604645e-8f;   // K * 2^-24
 
+// per-detection constants of the packed kernels (warp-uniform scalars)
+struct DetConst {
+    float td[6];       // the six target lengths (exact prologue values)
+    float T;           // |d_t|^2  (fast formulation only)
+    float G;           // d_t . d_m (fast formulation only)
+    float ms, msT;     // VERIFIED: K 2^-24 max_k |d_k|^2 and the same times T (margin scales, ray-scale invariant)
+    float fl[2], fm[2], fr[2], ft[2];   // fast formulation: rays rescaled to z = 1, (x, y) only; T, G, ms refer to these
+    float mc;          // VERIFIED: 2^-20 * (sum of the six target lengths), see finalize_margin
+};
+
+// fills the fast-formulation constants of a detection from its exact rays
+__device__ __forceinline__ void fast_constants(DetConst &D, const Detection<ExactF32> &det) {
+    const float zl = 1.0f / det.dl[2], zm = 1.0f / det.dm[2], zr = 1.0f / det.dr[2], zt = 1.0f / det.dt[2];
+    D.fl[0] = det.dl[0] * zl; D.fl[1] = det.dl[1] * zl;
+    D.fm[0] = det.dm[0] * zm; D.fm[1] = det.dm[1] * zm;
+    D.fr[0] = det.dr[0] * zr; D.fr[1] = det.dr[1] * zr;
+    D.ft[0] = det.dt[0] * zt; D.ft[1] = det.dt[1] * zt;
+    D.T = fmaf(D.ft[0], D.ft[0], fmaf(D.ft[1], D.ft[1], 1.0f));
+    D.G = fmaf(D.ft[0], D.fm[0], fmaf(D.ft[1], D.fm[1], 1.0f));
+    const float d0 = fmaf(D.fl[0], D.fl[0], fmaf(D.fl[1], D.fl[1], 1.0f));
+    const float d1 = fmaf(D.fm[0], D.fm[0], fmaf(D.fm[1], D.fm[1], 1.0f));
+    const float d2 = fmaf(D.fr[0], D.fr[0], fmaf(D.fr[1], D.fr[1], 1.0f));
+    D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
+    D.msT = D.ms * D.T;
+    D.mc = 9.5367431640625e-07f * (fabsf(D.td[0]) + fabsf(D.td[1]) + fabsf(D.td[2]) + fabsf(D.td[3]) + fabsf(D.td[4]) +
+                                  fabsf(D.td[5]));
+}
+
+struct PairResult;
+
+
+struct PairResult {
+    f2 r[6];           // signed residuals dist_k - target_k (abs is applied by the consumers)
+    f2 zc;             // z_dir_check
+    f2 m;              // VERIFIED mode: bound on |fast - exact| of the residual sum (see eval_pair_fast)
+    f2 za0, za2, zb0, zb2;   // lazy z_dir_check: the x/z components of X_l - X_m and X_r - X_m
+    __device__ __forceinline__ void finish_zc() { zc = fma2(za2, zb0, neg2(mul2(za0, zb2))); }
+};
+
+
+
 __device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, float b2, bool exact) {
     // (a0*b0 + a1*b1) + a2*b2, exact: three multiplies and two adds; fast: multiply + two FMAs
     if (exact) return add2(add2(mul2(a0, bc(b0)), mul2(a1, bc(b1))), mul2(a2, bc(b2)));
     return fma2(a2, bc(b2), fma2(a1, bc(b1), mul2(a0, bc(b0))));
 }
 
-// ---- EXACT: the canonical op order of oracle/fit_road_planes_ref.py, two planes at a time
-template <bool kSix>
-__device__ __forceinline__ void eval_pair(PackExact, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
-                                          PairResult &out) {
-    f2 X[4][3];
-    const float *rays[3] = {D.dl, D.dm, D.dr};
-    const f2 nd = neg2(d4);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        f2 t = dot3p(n0, n1, n2, rays[k][0], rays[k][1], rays[k][2], true);
-        f2 s = abs2(PackExact::div(nd, t));
-        X[k][0] = mul2(bc(rays[k][0]), s);
-        X[k][1] = mul2(bc(rays[k][1]), s);
-        X[k][2] = mul2(bc(rays[k][2]), s);
-    }
-    f2 ax = sub2(X[0][0], X[1][0]), az = sub2(X[0][2], X[1][2]);
-    f2 bx = sub2(X[2][0], X[1][0]), bz = sub2(X[2][2], X[1][2]);
-    out.zc = sub2(mul2(az, bx), mul2(ax, bz));
-    const float *dt = D.dt;
-    f2 c0 = sub2(mul2(n1, bc(dt[2])), mul2(n2, bc(dt[1])));
-    f2 c1 = sub2(mul2(n2, bc(dt[0])), mul2(n0, bc(dt[2])));
-    f2 c2 = sub2(mul2(n0, bc(dt[1])), mul2(n1, bc(dt[0])));
-    f2 p0 = sub2(mul2(bc(dt[1]), c2), mul2(bc(dt[2]), c1));
-    f2 p1 = sub2(mul2(bc(dt[2]), c0), mul2(bc(dt[0]), c2));
-    f2 p2 = sub2(mul2(bc(dt[0]), c1), mul2(bc(dt[1]), c0));
-    f2 num = add2(add2(mul2(p0, X[1][0]), mul2(p1, X[1][1])), mul2(p2, X[1][2]));
-    f2 den = add2(add2(mul2(p0, n0), mul2(p1, n1)), mul2(p2, n2));
-    f2 q = PackExact::div(num, den);
-    X[3][0] = sub2(X[1][0], mul2(q, n0));
-    X[3][1] = sub2(X[1][1], mul2(q, n1));
-    X[3][2] = sub2(X[1][2], mul2(q, n2));
-    const int pa[6] = {1, 0, 1, 0, 0, 2}, pb[6] = {3, 1, 2, 2, 3, 3};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        f2 dx = sub2(X[pa[k]][0], X[pb[k]][0]), dy = sub2(X[pa[k]][1], X[pb[k]][1]);
-        f2 dz = sub2(X[pa[k]][2], X[pb[k]][2]);
-        f2 dist = PackExact::sqrt(add2(add2(mul2(dx, dx), mul2(dy, dy)), mul2(dz, dz)));
-        out.r[k] = sub2(dist, bc(D.td[k]));
-    }
-}
-
 // ---- FAST: FMA contraction, MUFU reciprocal / square root, and algebra that is exact in real arithmetic.
-// All packed FP32 instructions (FFMA2 / FMUL2 / FADD2) retire 128 results/clk/SM like their scalar forms
-// (measured), so what counts is the number of FMA-pipe results per hypothesis.  With a unit normal n and
-// X_k = d_k |d / t_k| (t_k = n.d_k) every intersection point lies on the (+-) plane, n.X_k = |d| sign(t_k),
-// which removes most of calc_X_t:
-//   perp = d_t x (n x d_t) = n T - d_t u            (T = |d_t|^2, u = n.d_t)
-//   perp.n   = T - u^2
-//   perp.X_m = T |d| sign(t_m) - u s_m G            (G = d_t.d_m)
-//   X_t = X_m - q n,  |X_m - X_t| = |q|
-//   |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
-// 60 FMA-pipe results, 9 MUFU and ~11 ALU-pipe instructions per hypothesis (the direct formulation: 92 / 10).
+// All packed FP32 instructions (FFMA2 / FMUL2 / FADD2) retire 128 results/clk/SM like their scalar forms and the
+// loop is register-file-bandwidth bound (measured), so what counts is the number of instructions and operands
+// per hypothesis.
+//  * The rays are rescaled per detection to z = 1 (X_k = d_k |d / n.d_k| does not depend on the length of d_k),
+//    so every n.d_k is two FMAs and the z coordinate of X_k is the scale s_k itself.
+//  * With a unit normal n every intersection point lies on the (+-) plane, n.X_k = s_k t_k = |d| sign(t_k), which
+//    removes most of calc_X_t:
+//      perp = d_t x (n x d_t) = n T - d_t u           (T = |d_t|^2, u = n.d_t)
+//      perp.n   = T - u^2
+//      perp.X_m = s_m (T t_m - u G)                   (G = d_t.d_m)
+//      X_t = X_m - q n,  |X_m - X_t| = |q|
+//      |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
+//    and a.n = 0 unless the plane separates the rays, which is tested once per warp.
+// About 55 FMA-pipe results, 8-9 MUFU and ~6 ALU-pipe instructions per hypothesis (direct formulation: 92 / 10 / 17).
 template <bool kMergedRcp, bool kMargin, bool kLazyZ = false>
 __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
-    const f2 t0 = dot3p(n0, n1, n2, D.dl[0], D.dl[1], D.dl[2], false);
-    const f2 t1 = dot3p(n0, n1, n2, D.dm[0], D.dm[1], D.dm[2], false);
-    const f2 t2 = dot3p(n0, n1, n2, D.dr[0], D.dr[1], D.dr[2], false);
-    const f2 u = dot3p(n0, n1, n2, D.dt[0], D.dt[1], D.dt[2], false);
+    const f2 t0 = fma2(n0, bc(D.fl[0]), fma2(n1, bc(D.fl[1]), n2));
+    const f2 t1 = fma2(n0, bc(D.fm[0]), fma2(n1, bc(D.fm[1]), n2));
+    const f2 t2 = fma2(n0, bc(D.fr[0]), fma2(n1, bc(D.fr[1]), n2));
+    const f2 u = fma2(n0, bc(D.ft[0]), fma2(n1, bc(D.ft[1]), n2));
     const f2 den = fma2(neg2(u), u, bc(D.T));
     const f2 ad = abs2(d4);
     f2 i0, i1;
     if (kMergedRcp) {
-        // 1/t_l and 1/t_m from one MUFU.RCP (the MUFU unit, 16 results/clk/SM, is the other scarce pipe).  Only
-        // used once max-votes is known to be 6, where a degenerate (inf/NaN) hypothesis can neither win nor
-        // change max-votes.
+        // 1/t_l and 1/t_m from one MUFU.RCP.  Only used once max-votes is known to be 6, where a degenerate
+        // (inf/NaN) hypothesis can neither win nor change max-votes.
         const f2 inv = PackFast::rcp(mul2(t0, t1));
         i0 = mul2(inv, t1);
         i1 = mul2(inv, t0);
@@ -241,33 +216,40 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
     if (kMargin) {
         const f2 imax = pk(max3f(fabsf(lo(i0)), fabsf(lo(i1)), lo(i2)), max3f(fabsf(hi(i0)), fabsf(hi(i1)), hi(i2)));
         const f2 w = mul2(mul2(imax, imax), ad);                         // |d| / t_min^2
-        out.m = mul2(w, fma2(abs2(iden), bc(D.msT), bc(D.ms)));          // K u |d_k|^2 w (1 + T/|perp.n|)
+        out.m = fma2(w, fma2(abs2(iden), bc(D.msT), bc(D.ms)), bc(D.mc));   // K u |d_k|^2 w (1 + T/|perp.n|) + mc
     }
-    // n.X_k = |d| sign(t_k): sign transfer on the ALU pipe
-    const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
-    const f2 cs1 = pk(copysignf(lo(ad), lo(t1)), copysignf(hi(ad), hi(t1)));
-    const f2 cs2 = pk(copysignf(lo(ad), lo(t2)), copysignf(hi(ad), hi(t2)));
-    f2 a[3], b[3], c[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const f2 nxm = neg2(mul2(bc(D.dm[i]), s1));      // -X_m
-        a[i] = fma2(bc(D.dl[i]), s0, nxm);               // X_l - X_m
-        b[i] = fma2(bc(D.dr[i]), s2, nxm);               // X_r - X_m
-        c[i] = sub2(a[i], b[i]);                         // X_l - X_r
+    f2 a[3], b[3];
+    {
+        const f2 nx = neg2(mul2(bc(D.fm[0]), s1)), ny = neg2(mul2(bc(D.fm[1]), s1));      // -X_m (x, y)
+        a[0] = fma2(bc(D.fl[0]), s0, nx); a[1] = fma2(bc(D.fl[1]), s0, ny); a[2] = sub2(s0, s1);   // X_l - X_m
+        b[0] = fma2(bc(D.fr[0]), s2, nx); b[1] = fma2(bc(D.fr[1]), s2, ny); b[2] = sub2(s2, s1);   // X_r - X_m
     }
     if (kLazyZ) {           // z_dir_check is only formed for the few pairs that get that far (see the callers)
         out.za0 = a[0]; out.za2 = a[2]; out.zb0 = b[0]; out.zb2 = b[2];
     } else {
         out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
     }
-    const f2 num = fma2(mul2(u, s1), bc(-D.G), mul2(cs1, bc(D.T)));
-    const f2 q = mul2(num, iden);
+    const f2 q = mul2(mul2(s1, fma2(u, bc(-D.G), mul2(t1, bc(D.T)))), iden);
 #define GPP_SQN(v) fma2(v[2], v[2], fma2(v[1], v[1], mul2(v[0], v[0])))
-    const f2 na = GPP_SQN(a), nb = GPP_SQN(b), nc = GPP_SQN(c);
+    const f2 na = GPP_SQN(a), nb = GPP_SQN(b);
 #undef GPP_SQN
-    const f2 an = sub2(cs0, cs1), bn = sub2(cs2, cs1);
-    const f2 ne = fma2(q, fma2(an, bc(2.0f), q), na);    // |X_l - X_t|^2
-    const f2 nf = fma2(q, fma2(bn, bc(2.0f), q), nb);    // |X_r - X_t|^2
+    // |X_l - X_r|^2 from the difference itself (|a|^2 + |b|^2 - 2 a.b would cancel when X_l is close to X_r)
+    const f2 c0 = sub2(a[0], b[0]), c1 = sub2(a[1], b[1]), c2 = sub2(a[2], b[2]);
+    const f2 nc = fma2(c2, c2, fma2(c1, c1, mul2(c0, c0)));
+    // does the plane separate the rays (sign(t_l) or sign(t_r) != sign(t_m)) for any pair of this warp?
+    const unsigned sd = ((__float_as_uint(lo(t0)) ^ __float_as_uint(lo(t1))) | (__float_as_uint(lo(t2)) ^ __float_as_uint(lo(t1))) |
+                         (__float_as_uint(hi(t0)) ^ __float_as_uint(hi(t1))) | (__float_as_uint(hi(t2)) ^ __float_as_uint(hi(t1)))) >> 31;
+    f2 ne, nf;
+    if (__any_sync(0xffffffffu, sd != 0u)) {
+        const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
+        const f2 cs1 = pk(copysignf(lo(ad), lo(t1)), copysignf(hi(ad), hi(t1)));
+        const f2 cs2 = pk(copysignf(lo(ad), lo(t2)), copysignf(hi(ad), hi(t2)));
+        ne = fma2(q, fma2(sub2(cs0, cs1), bc(2.0f), q), na);             // |X_l - X_t|^2
+        nf = fma2(q, fma2(sub2(cs2, cs1), bc(2.0f), q), nb);             // |X_r - X_t|^2
+    } else {
+        ne = fma2(q, q, na);
+        nf = fma2(q, q, nb);
+    }
     out.r[0] = sub2(abs2(q), bc(D.td[0]));
     out.r[1] = sub2(PackFast::sqrt(na), bc(D.td[1]));
     out.r[2] = sub2(PackFast::sqrt(nb), bc(D.td[2]));
@@ -281,6 +263,11 @@ __device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2
     eval_pair_fast<kSix, false>(D, n0, n1, n2, d4, out);
 }
 
+// The geometric margin of eval_pair_fast covers the error of the 3-D points.  The six distances, their
+// differences to the targets and the residual sum are additionally rounded at their own magnitude
+// (<= R + sum of targets): 16 ulp of that are added.
+__device__ __forceinline__ void finalize_margin(PairResult &h, f2 R, const DetConst &D);
+
 // residual sum ((((|r0|+|r1|)+|r2|)+|r3|)+|r4|)+|r5| for both planes of the pair
 __device__ __forceinline__ f2 resid_sum(const PairResult &h) {
     f2 s = add2(abs2(h.r[0]), abs2(h.r[1]));
@@ -289,6 +276,9 @@ __device__ __forceinline__ f2 resid_sum(const PairResult &h) {
     s = add2(s, abs2(h.r[4]));
     s = add2(s, abs2(h.r[5]));
     return s;
+}
+__device__ __forceinline__ void finalize_margin(PairResult &h, f2 R, const DetConst &) {
+    h.m = fma2(R, bc(9.5367431640625e-07f), h.m);             // eval_pair_fast already added the mc term
 }
 __device__ __forceinline__ int votes_of(float r0, float r1, float r2, float r3, float r4, float r5) {
     const float thr = 0.7f;   // where(greater(|r|, thr), 0, 1): NaN is not greater -> a vote (:31)
@@ -408,6 +398,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
     const long long n_groups = kSplit ? n_work : (n_work + kWarps - 1) / kWarps;
     unsigned int *claim = reinterpret_cast<unsigned int *>(partial + 2 * kWarps);       // [2]: groups k, k+1
+    float *detx = reinterpret_cast<float *>(claim + 2) + (threadIdx.x >> 5) * 20;       // this warp's exact constants
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -458,22 +449,33 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
         if (args.det_list) mm = args.det_list[mm];
         const long long m = w_id < n_work ? mm : args.n_det;       // >= n_det: nothing is written
+        // The exact per-detection constants are only needed by the rare exact paths (verification batches, the
+        // epilogue): they are parked in this warp's shared-memory slot and re-read there (GPP_LOAD_DET) instead
+        // of occupying 18 registers in the loop.
+#define GPP_LOAD_DET(det)                                                                   \
+    Detection<ExactF32> det;                                                                \
+    _Pragma("unroll") for (int i_ = 0; i_ < 3; ++i_) {                                      \
+        det.dl[i_] = detx[i_]; det.dm[i_] = detx[3 + i_]; det.dr[i_] = detx[6 + i_]; det.dt[i_] = detx[9 + i_]; \
+    }                                                                                       \
+    _Pragma("unroll") for (int i_ = 0; i_ < 6; ++i_) det.td[i_] = detx[12 + i_]
         DetConst D;
-        Detection<ExactF32> det;             // same registers as D (the copies below are free)
-        load_detection<ExactF32, ExactF32>(det, args.boxes + 12 * mm, args.dims + 3 * mm,
-                                           __ldg(args.orient + mm), args.pinv + 12 * (mm / args.dets_per_image));
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { D.dl[i] = det.dl[i]; D.dm[i] = det.dm[i]; D.dr[i] = det.dr[i]; D.dt[i] = det.dt[i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
-        D.T = fmaf(det.dt[2], det.dt[2], fmaf(det.dt[1], det.dt[1], det.dt[0] * det.dt[0]));
-        D.G = fmaf(det.dt[2], det.dm[2], fmaf(det.dt[1], det.dm[1], det.dt[0] * det.dm[0]));
         {
-            const float d0 = det.dl[0] * det.dl[0] + det.dl[1] * det.dl[1] + det.dl[2] * det.dl[2];
-            const float d1 = det.dm[0] * det.dm[0] + det.dm[1] * det.dm[1] + det.dm[2] * det.dm[2];
-            const float d2 = det.dr[0] * det.dr[0] + det.dr[1] * det.dr[1] + det.dr[2] * det.dr[2];
-            D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
-            D.msT = D.ms * D.T;
+            Detection<ExactF32> det0;
+            load_detection<ExactF32, ExactF32>(det0, args.boxes + 12 * mm, args.dims + 3 * mm, __ldg(args.orient + mm),
+                                               args.pinv + 12 * (mm / args.dets_per_image));
+#pragma unroll
+            for (int i = 0; i < 6; ++i) D.td[i] = det0.td[i];
+            fast_constants(D, det0);
+            __syncwarp();                            // the previous detection's readers are done
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    detx[i] = det0.dl[i]; detx[3 + i] = det0.dm[i]; detx[6 + i] = det0.dr[i]; detx[9 + i] = det0.dt[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) detx[12 + i] = det0.td[i];
+            }
+            __syncwarp();
         }
 
         LaneState<float> st;                 // general mode (max votes not yet known to be 6)
@@ -538,10 +540,12 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         // the residual test comes first: once the warp's best is good, almost no pair passes it,
                         // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp
                         eval_pair_fast<true, true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                        const f2 Rlo = sub2(resid_sum(h), h.m);         // lower bound of the residual sum
+                        const f2 R = resid_sum(h);
+                        const f2 Rlo = fma2(R, bc(0.99999905f), neg2(h.m));   // R - (m + 2^-20 R): lower bound of the sum
                         trig0 = !(lo(Rlo) > wbest);
                         trig1 = !(hi(Rlo) > wbest);
                         if (__any_sync(0xffffffffu, trig0 || trig1)) {
+                            finalize_margin(h, R, D);
                             h.finish_zc();
                             const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
                                              rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
@@ -555,6 +559,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                     } else {
                         eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
+                        finalize_margin(h, R, D);
                         const f2 Rlo = sub2(R, h.m);
                         const f2 zhi = z_upper(h, D);
                         const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
@@ -574,6 +579,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         __syncwarp();
                         const bool flush_all = __any_sync(0xffffffffu, urgent);
                         if (qn >= 32 || flush_all) {
+                            GPP_LOAD_DET(det);
                             while (qn >= 32) {
                                 qn -= 32;
                                 verify_general(det, args.planes, queue[qn + lane], st);
@@ -608,6 +614,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
             __syncwarp();
         }
 
+        GPP_LOAD_DET(det);                           // exact constants for the rest of this detection
         if (kVerified) {
             if (lane < qn) verify_general(det, args.planes, queue[lane], st);   // the last partial batch
             qn = 0;
