@@ -252,11 +252,14 @@ def main():
         out = poller.fit_torch(tb, td, to, tp, mode=args.mode)
         return out
 
+    # nvidia-smi's start-up takes a driver lock that stalls a running kernel for tens of ms: start the sampler
+    # BEFORE the warm-up steps so that only its steady 100 ms polling overlaps the timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.5)
     for _ in range(args.warmup):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = poller.launch_count()
     t_clock0 = time.time()
     kernel_ms = []
@@ -364,6 +367,7 @@ def main():
             'cpu_baseline': cpu,
             'other_modes': dict(other_modes, unit=UNIT),
             'wall_ms_per_step_device_leg': 1e3 * wall_dev / args.steps,
+            'kernel_ms_steps': [round(x, 3) for x in kernel_ms],
         }
         print(json.dumps(line))
     if world > 1:

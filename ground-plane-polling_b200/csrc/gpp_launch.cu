@@ -174,21 +174,33 @@ static bool use_split(const gpp_handle *h, long long n_det) {
     return n_det < 4LL * h->sm_count * 3;
 }
 
-static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_handle::WorkSlot **out) {
-    gpp_handle::WorkSlot &w = h->work[h->next_work++ % gpp_handle::kWorkSlots];
-    cudaError_t e = cudaSuccess;
-    if (!w.done) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
-    if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, 4 * sizeof(unsigned int));
-    if (e == cudaSuccess && w.used) e = cudaStreamWaitEvent(s, w.done, 0);   // previous user of this slot
-    if (e == cudaSuccess && n_det > w.cap) {
-        // cudaMalloc/cudaFree are not stream-ordered: the previous user must be finished on the host side too
-        if (w.used) e = cudaEventSynchronize(w.done);
-        if (e == cudaSuccess) { cudaFree(w.list); cudaFree(w.ulist); cudaFree(w.unique); w.list = w.ulist = nullptr; w.unique = nullptr; w.cap = 0; }
+// All work-list slots are (re)allocated together, so that a steady stream of calls never hits cudaMalloc (which
+// is not stream-ordered and would stall the GPU inside the caller's timed region) after the first one.
+static int grow_worklists(gpp_handle *h, long long n_det) {
+    cudaError_t e = cudaDeviceSynchronize();      // earlier launches may still use the old buffers
+    for (int i = 0; i < gpp_handle::kWorkSlots && e == cudaSuccess; ++i) {
+        gpp_handle::WorkSlot &w = h->work[i];
+        cudaFree(w.list); cudaFree(w.ulist); cudaFree(w.unique);
+        w.list = w.ulist = nullptr; w.unique = nullptr; w.cap = 0; w.used = false;
+        if (!w.done) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
+        if (e == cudaSuccess && !w.count) e = cudaMalloc(&w.count, 4 * sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMalloc(&w.list, sizeof(long long) * (size_t)n_det);
         if (e == cudaSuccess) e = cudaMalloc(&w.ulist, sizeof(long long) * (size_t)n_det);
         if (e == cudaSuccess) e = cudaMalloc(&w.unique, (size_t)n_det);
         if (e == cudaSuccess) w.cap = n_det;
     }
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "work list allocation: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+static int reserve_worklist(gpp_handle *h, long long n_det, cudaStream_t s, gpp_handle::WorkSlot **out) {
+    if (n_det > h->work[0].cap) {
+        int rc = grow_worklists(h, n_det + n_det / 4);
+        if (rc) return rc;
+    }
+    gpp_handle::WorkSlot &w = h->work[h->next_work++ % gpp_handle::kWorkSlots];
+    cudaError_t e = cudaSuccess;
+    if (w.used) e = cudaStreamWaitEvent(s, w.done, 0);        // previous user of this slot
     if (e == cudaSuccess) e = cudaMemsetAsync(w.count, 0, 4 * sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "work list setup: %s", cudaGetErrorString(e));
     *out = &w;

@@ -6,6 +6,10 @@
 #pragma once
 #include "gpp_math.cuh"
 
+#ifndef GPP_WAIT_SLEEP_NS
+#define GPP_WAIT_SLEEP_NS 200
+#endif
+
 namespace gpp {
 
 // ------------------------------------------------------------------ mbarrier / TMA (1-D bulk) helpers
@@ -25,17 +29,34 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Waiting warps should not steal issue slots from the working ones (the kernels are issue / register-file
+// bound): after a failed try_wait the warp sleeps a little before polling again.  (A long suspend-time hint on
+// try_wait itself was measured to delay the wake-up far more than it saves.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if GPP_WAIT_SLEEP_NS == 0
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "GPP_WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra GPP_DONE_%=;\n"
-        "bra GPP_WAIT_%=;\n"
-        "GPP_DONE_%=:\n"
+        "@!p bra GPP_WAIT_%=;\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+    return;
+#endif
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GPP_DONE_%=;\n"
+        "GPP_WAIT_%=:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra GPP_WAIT_%=;\n"
+        "GPP_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(GPP_WAIT_SLEEP_NS)
         : "memory");
 }
 // global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (complete_tx).
