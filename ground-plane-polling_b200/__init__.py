@@ -11,6 +11,11 @@ from . import _lib  # noqa: F401
 from .layers import fit_road_planes as _frp_module  # noqa: F401
 from .layers.fit_road_planes import (FitRoadPlanes, PlanePoller, fit_road_planes, fit_road_planes_dlpack,  # noqa: F401
                                      fit_road_planes_torch, get_poller)
+from .layers._misc import RegressBoxes, RegressDims, decode, decode_torch  # noqa: F401
+from .layers.filter_detections import (FilterDetections, filter_detections, filter_detections_batch,  # noqa: F401
+                                       filter_detections_torch)
+from . import pipeline  # noqa: F401
+from .pipeline import detections_from_heads  # noqa: F401
 from .utils import synthetic  # noqa: F401
 from .utils import pose  # noqa: F401
 from .utils.pose import recover_pose, recover_pose_torch  # noqa: F401

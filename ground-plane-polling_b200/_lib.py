@@ -42,6 +42,14 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     'gpp_kitti_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]),
     'gpp_kitti_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p, c_void_p]),
+    'gpp_decode_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    'gpp_decode_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    'gpp_filter_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'gpp_filter_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'gpp_last_kernel_ms': (c_int, [c_void_p, c_float_p]),
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),

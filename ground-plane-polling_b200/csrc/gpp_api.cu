@@ -147,6 +147,9 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->d_planes32);
     cudaFree(h->d_planes64);
     cudaFree(h->d_pairs);
+    cudaFree(h->filter_keys);
+    cudaFree(h->filter_orient);
+    cudaFree(h->filter_counts);
     for (auto &w : h->work) {
         cudaFree(w.list);
         cudaFree(w.ulist);

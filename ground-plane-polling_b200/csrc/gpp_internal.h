@@ -63,6 +63,12 @@ struct gpp_handle {
     int timing_chunks = 0;
     bool timing_single = false;
     int64_t launches = 0;
+    // FilterDetections scratch (gpp_detect.cu): candidate keys, per-anchor orientation, per-image counters
+    unsigned long long *filter_keys = nullptr;
+    unsigned char *filter_orient = nullptr;
+    unsigned int *filter_counts = nullptr;
+    size_t filter_keys_bytes = 0, filter_orient_bytes = 0;
+    int filter_counts_n = 0;
     // launch configuration (filled by configure_kernels; the force_* fields are a tuning hook)
     int force_variant = 0, force_ctas_per_sm = 0;
     int occ[3] = {0, 0, 0};                      // resident CTAs per SM: exact dpw 1, exact dpw 2, fp64

@@ -124,6 +124,33 @@ int gpp_kitti_host(gpp_handle *h, const float *locations, const float *angles, c
 int gpp_kitti_device(gpp_handle *h, const float *locations, const float *angles, const float *dimensions, long n,
                      float *out, void *stream);
 
+/* ---- the two steps before polling in the reference's inference graph ----
+ *
+ * Decode: RegressBoxes + RegressDims (layers/_misc.py:132-140, :185-186; backend/common.py:23-84).
+ *   anchors A*4 (x1,y1,x2,y2), regression B*A*12, classification B*A*8 (sets the sign of the middle / top key-point
+ *   x offsets), regression_dim B*A*3  ->  boxes B*A*12, dimensions B*A*3.
+ *   box_mean_std: 24 floats (12 means then 12 stds) or NULL for the layer defaults; dim_mean_std: 6 floats or NULL. */
+int gpp_decode_host(gpp_handle *h, const float *anchors, const float *regression, const float *classification,
+                    const float *regression_dim, int B, int A, const float *box_mean_std, const float *dim_mean_std,
+                    float *boxes, float *dimensions);
+int gpp_decode_device(gpp_handle *h, const float *anchors, const float *regression, const float *classification,
+                      const float *regression_dim, int B, int A, const float *box_mean_std, const float *dim_mean_std,
+                      float *boxes, float *dimensions, void *stream);
+
+/* FilterDetections (layers/filter_detections.py:18-189) for the configuration the model is built with
+ * (models/retinanet.py:415): one class, class_specific_filter, orientation taken as the arg-max, NMS on.
+ * Per image: score = max over the 8 classification values, orientation = arg-max over the 4 (halves merged by max),
+ * keep score > score_threshold, greedy NMS (IoU > nms_threshold suppresses; descending score, ties by lower anchor
+ * index) up to max_detections (<= 128), rows sorted by score, padded with -1.
+ *   out_boxes B*max*12, out_dimensions B*max*3, out_scores B*max, out_labels / out_orientations B*max int32. */
+int gpp_filter_host(gpp_handle *h, const float *boxes, const float *dimensions, const float *classification, int B,
+                    int A, float score_threshold, float nms_threshold, int max_detections, float *out_boxes,
+                    float *out_dimensions, float *out_scores, int32_t *out_labels, int32_t *out_orientations);
+int gpp_filter_device(gpp_handle *h, const float *boxes, const float *dimensions, const float *classification, int B,
+                      int A, float score_threshold, float nms_threshold, int max_detections, float *out_boxes,
+                      float *out_dimensions, float *out_scores, int32_t *out_labels, int32_t *out_orientations,
+                      void *stream);
+
 /* Measurement helpers (bench.py): time of the last gpp_fit_* polling kernel(s) in milliseconds, measured
  * with CUDA events on the launching stream (valid after the stream has been synchronised); number of
  * kernels launched by this handle so far. */

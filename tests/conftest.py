@@ -20,7 +20,7 @@ def load_planes(tag):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('detect_'))
 
 
 def load_golden(name):
