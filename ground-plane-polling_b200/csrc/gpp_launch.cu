@@ -264,7 +264,7 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
         const ulonglong2 v0 = pairs[2 * p], v1 = pairs[2 * p + 1];
         PairResult h;
-        eval_pair_fast<kSix, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+        eval_pair_fast<kSix, 1>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
         const f2 R = resid_sum(h);
         finalize_margin(h, R, D);
         const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));

@@ -189,7 +189,8 @@ __device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, flo
 //      |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
 //    and a.n = 0 unless the plane separates the rays, which is tested once per warp.
 // About 55 FMA-pipe results, 8-9 MUFU and ~6 ALU-pipe instructions per hypothesis (direct formulation: 92 / 10 / 17).
-template <bool kMergedRcp, bool kMargin, bool kLazyZ = false>
+// kMargin: 0 = none, 1 = out.m = geometric margin + mc, 2 = geometric margin only (the caller accounts for mc)
+template <bool kMergedRcp, int kMargin, bool kLazyZ = false>
 __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
     const f2 t0 = fma2(n0, bc(D.fl[0]), fma2(n1, bc(D.fl[1]), n2));
     const f2 t1 = fma2(n0, bc(D.fm[0]), fma2(n1, bc(D.fm[1]), n2));
@@ -216,7 +217,8 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
     if (kMargin) {
         const f2 imax = pk(max3f(fabsf(lo(i0)), fabsf(lo(i1)), lo(i2)), max3f(fabsf(hi(i0)), fabsf(hi(i1)), hi(i2)));
         const f2 w = mul2(mul2(imax, imax), ad);                         // |d| / t_min^2
-        out.m = fma2(w, fma2(abs2(iden), bc(D.msT), bc(D.ms)), bc(D.mc));   // K u |d_k|^2 w (1 + T/|perp.n|) + mc
+        const f2 g = fma2(abs2(iden), bc(D.msT), bc(D.ms));             // K u |d_k|^2 (1 + T/|perp.n|)
+        out.m = kMargin == 1 ? fma2(w, g, bc(D.mc)) : mul2(w, g);
     }
     f2 a[3], b[3];
     {
@@ -241,9 +243,9 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
                          (__float_as_uint(hi(t0)) ^ __float_as_uint(hi(t1))) | (__float_as_uint(hi(t2)) ^ __float_as_uint(hi(t1)))) >> 31;
     f2 ne, nf;
     if (__any_sync(0xffffffffu, sd != 0u)) {
-        const f2 cs0 = pk(copysignf(lo(ad), lo(t0)), copysignf(hi(ad), hi(t0)));
-        const f2 cs1 = pk(copysignf(lo(ad), lo(t1)), copysignf(hi(ad), hi(t1)));
-        const f2 cs2 = pk(copysignf(lo(ad), lo(t2)), copysignf(hi(ad), hi(t2)));
+        const f2 cs0 = pk(copysignf(lo(d4), lo(t0)), copysignf(hi(d4), hi(t0)));
+        const f2 cs1 = pk(copysignf(lo(d4), lo(t1)), copysignf(hi(d4), hi(t1)));
+        const f2 cs2 = pk(copysignf(lo(d4), lo(t2)), copysignf(hi(d4), hi(t2)));
         ne = fma2(q, fma2(sub2(cs0, cs1), bc(2.0f), q), na);             // |X_l - X_t|^2
         nf = fma2(q, fma2(sub2(cs2, cs1), bc(2.0f), q), nb);             // |X_r - X_t|^2
     } else {
@@ -260,7 +262,7 @@ __device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, 
 template <bool kSix>
 __device__ __forceinline__ void eval_pair(PackFast, const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4,
                                           PairResult &out) {
-    eval_pair_fast<kSix, false>(D, n0, n1, n2, d4, out);
+    eval_pair_fast<kSix, 0>(D, n0, n1, n2, d4, out);
 }
 
 // The geometric margin of eval_pair_fast covers the error of the 3-D points.  The six distances, their
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         b6.bestR = FLT_MAX; b6.bestIdx = 0;
         bool m6 = false;
         float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
+        float wthr = __int_as_float(0x7f800000);   // VERIFIED: (wbest + mc)(1 + 2^-18), see the all-six phase
         int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
         int Mcur = -1;                       // VERIFIED: exact max-votes so far in this warp (warp-uniform)
 
@@ -538,26 +541,27 @@ GPP_UNROLL(GPP_M6_UNROLL)
                     bool trig0, trig1, urgent = false;
                     if (Mcur == 6) {
                         // the residual test comes first: once the warp's best is good, almost no pair passes it,
-                        // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp
-                        eval_pair_fast<true, true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp.
+                        // skip iff R (1 - 2^-20) - m_geo - mc > wbest; tested as R - m_geo > wthr with the
+                        // warp-uniform wthr = (wbest + mc)(1 + 2^-18), which implies it (m_geo >= 0)
+                        eval_pair_fast<true, 2, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
-                        const f2 Rlo = fma2(R, bc(0.99999905f), neg2(h.m));   // R - (m + 2^-20 R): lower bound of the sum
-                        trig0 = !(lo(Rlo) > wbest);
-                        trig1 = !(hi(Rlo) > wbest);
-                        if (__any_sync(0xffffffffu, trig0 || trig1)) {
-                            finalize_margin(h, R, D);
-                            h.finish_zc();
-                            const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                                             rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
-                            const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
-                            const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
-                            trig0 = trig0 && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
-                            trig1 = trig1 && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
-                        } else {
-                            trig0 = trig1 = false;
-                        }
+                        const f2 Rlo = sub2(R, h.m);
+                        trig0 = !(lo(Rlo) > wthr);
+                        trig1 = !(hi(Rlo) > wthr);
+                        if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
+                        h.m = add2(h.m, bc(D.mc));
+                        finalize_margin(h, R, D);
+                        h.finish_zc();
+                        const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                                         rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+                        const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
+                        const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
+                        const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
+                        trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
+                        trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
                     } else {
-                        eval_pair_fast<false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        eval_pair_fast<false, 1>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
                         finalize_margin(h, R, D);
                         const f2 Rlo = sub2(R, h.m);
@@ -592,10 +596,11 @@ GPP_UNROLL(GPP_M6_UNROLL)
                             Mcur = __reduce_max_sync(0xffffffffu, st.M);
                             wbest = __uint_as_float(__reduce_min_sync(
                                 0xffffffffu, __float_as_uint(st.M == Mcur ? st.bestR : FLT_MAX)));
+                            wthr = (wbest + D.mc) * 1.0000038f;
                         }
                     }
                 } else {
-                    eval_pair_fast<true, false, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    eval_pair_fast<true, 0, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                     const f2 R = resid_sum(h);
                     // only a pair that scores no worse than the warp's best so far can change the result
                     if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
