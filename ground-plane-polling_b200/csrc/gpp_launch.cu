@@ -1,5 +1,8 @@
 // Kernel instantiations and launch configuration of the polling kernels (gpp_poll2.cuh: packed-pair fp32
 // modes; gpp_poll.cuh: scalar kernel, used for the FP64 verify mode).
+#ifdef GPP_STATS
+#include <cstdio>
+#endif
 #include "../../include/gpp.h"
 #include "gpp_internal.h"
 
@@ -330,6 +333,19 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
                 GPP_K_VERIFIED_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[2]), kWarps * 32, kSmem2, s>>>(b);
             } else {
                 verified_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ3[v]), kWarps * 32, kSmem2, s>>>(b);
+#ifdef GPP_STATS
+                {
+                    unsigned long long st[8], zero[8] = {0};
+                    cudaDeviceSynchronize();
+                    cudaMemcpyFromSymbol(st, g_stats, sizeof(st));
+                    cudaMemcpyToSymbol(g_stats, zero, sizeof(zero));
+                    const double rows = double(st[0] + st[1] + st[2]);
+                    fprintf(stderr, "[gpp stats] dets %llu rows/det %.1f: all-six %.1f%% (pass %.2f%%), general>=4 %.1f%% <4 %.1f%% (pass %.2f%% of all rows); "
+                            "exact verifications/det %.1f, flushes/det %.2f\n", st[7], rows / st[7], 100.0 * st[0] / rows,
+                            100.0 * st[3] / rows, 100.0 * st[1] / rows, 100.0 * st[2] / rows, 100.0 * st[4] / rows,
+                            double(st[5]) / st[7], double(st[6]) / st[7]);
+                }
+#endif
             }
         } else if (split) {
             GPP_K_FAST_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[1]), kWarps * 32, kSmem2, s>>>(b);

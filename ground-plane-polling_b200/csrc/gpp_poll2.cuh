@@ -335,6 +335,16 @@ __device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n
 
 constexpr int kVerifyQueue = 96;
 
+// development counters (only with -DGPP_STATS; printed by launch_poll_f32): rows in the all-six phase, rows in
+// the general phase with Mcur >= 4 / < 4, rows that passed the cheap test (all-six, general), exact
+// verifications, flushes, detections
+#ifdef GPP_STATS
+__device__ unsigned long long g_stats[8];
+#define GPP_STAT(i, n) (st_cnt[i] += (n))
+#else
+#define GPP_STAT(i, n) ((void)0)
+#endif
+
 // VERIFIED: exact re-evaluation of one queued plane with the full (max-votes, residual, index) bookkeeping;
 // ties break by index explicitly (the queue is not drained in index order)
 __device__ __forceinline__ void verify_general(const Detection<ExactF32> &de, const float4 *__restrict__ planes, int j,
@@ -366,6 +376,18 @@ __device__ __forceinline__ int loose_votes(const PairResult &h, bool upper) {
         const float rk = upper ? hi(h.r[k]) : lo(h.r[k]);
         const float mk = upper ? hi(h.m) : lo(h.m);
         v += int(!(fabsf(rk) - mk > thr));
+    }
+    return v;
+}
+
+__device__ __forceinline__ int strict_votes(const PairResult &h, bool upper) {
+    const float thr = 0.7f;   // votes that are certain within the margin: |r_k| + m <= thr (NaN never counts)
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float rk = upper ? hi(h.r[k]) : lo(h.r[k]);
+        const float mk = upper ? hi(h.m) : lo(h.m);
+        v += int(fabsf(rk) + mk <= thr);
     }
     return v;
 }
@@ -489,6 +511,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         float wthr = __int_as_float(0x7f800000);   // VERIFIED: (wbest + mc)(1 + 2^-18), see the all-six phase
         int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
         int Mcur = -1;                       // VERIFIED: exact max-votes so far in this warp (warp-uniform)
+#ifdef GPP_STATS
+        unsigned int st_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+#endif
 
         for (int t = 0; t < n_tiles; ++t, ++it) {
             const int s = int(it % kStages);
@@ -544,6 +569,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp.
                         // skip iff R (1 - 2^-20) - m_geo - mc > wbest; tested as R - m_geo > wthr with the
                         // warp-uniform wthr = (wbest + mc)(1 + 2^-18), which implies it (m_geo >= 0)
+                        GPP_STAT(0, 1);
                         eval_pair_fast<true, 2, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
                         const f2 Rlo = sub2(R, h.m);
@@ -552,23 +578,79 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
                         h.m = add2(h.m, bc(D.mc));
                         finalize_margin(h, R, D);
-                        h.finish_zc();
                         const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
                                          rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
                         const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
+                        // a best residual sum above 0.7 also lets planes with fewer than six votes through the
+                        // residual test: drop them before the z-check / queue work
+                        trig0 = trig0 && !(lo(rlo) > 0.7f);
+                        trig1 = trig1 && !(hi(rlo) > 0.7f);
+                        if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
+                        GPP_STAT(3, 1);
+                        h.finish_zc();
                         const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
                         const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
+                        {
+                            // A plane that CERTAINLY has six votes and passes the z-check bounds the final best
+                            // residual by its own upper bound R + m: lower the threshold right away instead of
+                            // waiting for the next exact batch (the plane itself stays queued and is verified).
+                            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+                            const f2 rhi = add2(rm, h.m);
+                            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+                            const float e0 = (lo(rhi) <= 0.7f && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX) ? lo(Rhi) : FLT_MAX;
+                            const float e1 = (hi(rhi) <= 0.7f && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX) ? hi(Rhi) : FLT_MAX;
+                            const float e = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(e0, e1))));
+                            if (e < wbest) {
+                                wbest = e;
+                                wthr = (wbest + D.mc) * 1.0000038f;
+                            }
+                        }
                         trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
                         trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
                     } else {
-                        eval_pair_fast<false, 1>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                        GPP_STAT(Mcur >= 4 ? 1 : 2, 1);
+                        eval_pair_fast<false, 1, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
                         const f2 R = resid_sum(h);
                         finalize_margin(h, R, D);
                         const f2 Rlo = sub2(R, h.m);
+                        if (Mcur >= 4) {
+                            // cheap necessary condition first (warp-uniform skip, like the all-six phase).  With
+                            // p_i = max(|r_2i|, |r_2i+1|):  six votes => max p <= thr,  >= five votes => median p <= thr
+                            // (at most one residual, hence at most one pair, exceeds),  >= four votes => min p <= thr.
+                            // The pair matters only if it may have MORE votes than Mcur, or as many and a residual
+                            // sum no worse than the best.
+                            const f2 p0 = pk(fmaxf(fabsf(lo(h.r[0])), fabsf(lo(h.r[1]))), fmaxf(fabsf(hi(h.r[0])), fabsf(hi(h.r[1]))));
+                            const f2 p1 = pk(fmaxf(fabsf(lo(h.r[2])), fabsf(lo(h.r[3]))), fmaxf(fabsf(hi(h.r[2])), fabsf(hi(h.r[3]))));
+                            const f2 p2 = pk(fmaxf(fabsf(lo(h.r[4])), fabsf(lo(h.r[5]))), fmaxf(fabsf(hi(h.r[4])), fabsf(hi(h.r[5]))));
+                            const f2 pmax = pk(max3f(lo(p0), lo(p1), lo(p2)), max3f(hi(p0), hi(p1), hi(p2)));
+                            const f2 pmin = pk(fminf(fminf(lo(p0), lo(p1)), lo(p2)), fminf(fminf(hi(p0), hi(p1)), hi(p2)));
+                            const f2 pmed = pk(fmaxf(fminf(lo(p0), lo(p1)), fminf(fmaxf(lo(p0), lo(p1)), lo(p2))),
+                                               fmaxf(fminf(hi(p0), hi(p1)), fminf(fmaxf(hi(p0), hi(p1)), hi(p2))));
+                            const f2 more = sub2(Mcur == 5 ? pmax : pmed, h.m);      // > 0.7: cannot have more votes
+                            const f2 same = sub2(Mcur == 5 ? pmed : pmin, h.m);      // > 0.7: cannot have as many
+                            const bool nan0 = !(lo(R) == lo(R)), nan1 = !(hi(R) == hi(R));   // degenerate: full test
+                            const bool may0 = nan0 || !(lo(more) > 0.7f) || (!(lo(same) > 0.7f) && !(lo(Rlo) > wbest));
+                            const bool may1 = nan1 || !(hi(more) > 0.7f) || (!(hi(same) > 0.7f) && !(hi(Rlo) > wbest));
+                            if (!__any_sync(0xffffffffu, may0 || may1)) continue;
+                        }
+                        GPP_STAT(4, 1);
+                        h.finish_zc();
                         const f2 zhi = z_upper(h, D);
                         const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
-                        trig0 = (V0 > Mcur) || (V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest));
-                        trig1 = (V1 > Mcur) || (V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest));
+                        const bool k0 = V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
+                        const bool k1 = V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+                        if (Mcur >= 4 && __any_sync(0xffffffffu, k0 || k1)) {
+                            // same early bound as in the all-six phase: exactly Mcur votes for certain, z-check passed
+                            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+                            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+                            const bool c0 = k0 && strict_votes(h, false) == Mcur && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX;
+                            const bool c1 = k1 && strict_votes(h, true) == Mcur && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX;
+                            const float e = __uint_as_float(__reduce_min_sync(
+                                0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
+                            wbest = fminf(wbest, e);
+                        }
+                        trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
+                        trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
                         urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
                     }
                     const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
@@ -583,6 +665,8 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         __syncwarp();
                         const bool flush_all = __any_sync(0xffffffffu, urgent);
                         if (qn >= 32 || flush_all) {
+                            GPP_STAT(6, 1);
+                            GPP_STAT(5, qn);
                             GPP_LOAD_DET(det);
                             while (qn >= 32) {
                                 qn -= 32;
@@ -593,9 +677,11 @@ GPP_UNROLL(GPP_M6_UNROLL)
                                 qn = 0;
                             }
                             __syncwarp();
-                            Mcur = __reduce_max_sync(0xffffffffu, st.M);
-                            wbest = __uint_as_float(__reduce_min_sync(
-                                0xffffffffu, __float_as_uint(st.M == Mcur ? st.bestR : FLT_MAX)));
+                            const int Mnew = __reduce_max_sync(0xffffffffu, st.M);
+                            const float wnew = __uint_as_float(__reduce_min_sync(
+                                0xffffffffu, __float_as_uint(st.M == Mnew ? st.bestR : FLT_MAX)));
+                            wbest = (Mnew == Mcur) ? fminf(wbest, wnew) : wnew;   // early bounds stay valid at the same max-votes
+                            Mcur = Mnew;
                             wthr = (wbest + D.mc) * 1.0000038f;
                         }
                     }
@@ -621,7 +707,12 @@ GPP_UNROLL(GPP_M6_UNROLL)
 
         GPP_LOAD_DET(det);                           // exact constants for the rest of this detection
         if (kVerified) {
+            GPP_STAT(5, qn);
             if (lane < qn) verify_general(det, args.planes, queue[lane], st);   // the last partial batch
+#ifdef GPP_STATS
+            if (lane == 0)
+                for (int i = 0; i < 8; ++i) atomicAdd(&g_stats[i], (unsigned long long)st_cnt[i]);
+#endif
             qn = 0;
             __syncwarp();
             m6 = false;                              // the epilogue takes (max-votes, best) from `st`
