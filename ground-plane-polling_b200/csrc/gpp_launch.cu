@@ -16,7 +16,11 @@
 namespace gpp {
 
 // CTA shape: 8 warps, 1024-plane tiles (32 KB fp32 pairs / 32 KB fp64), 3-stage TMA ring.
-constexpr int kWarps = 8;
+#ifndef GPP_WARPS
+#define GPP_WARPS 8
+#endif
+constexpr int kWarps = GPP_WARPS;
+#define GPP_MB(x) ((x) * 8 / GPP_WARPS)   /* resident CTAs per SM for x CTAs of 8 warps */
 #ifndef GPP_TILE
 #define GPP_TILE 1024
 #endif
@@ -134,8 +138,8 @@ constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * s
 #define GPP_K_EXACT1 poll_kernel<ExactF32, kWarps, 1, kTile32, kStages>
 #define GPP_K_EXACT2 poll_kernel<ExactF32, kWarps, 2, kTile32, kStages>
 #define GPP_K_EXACT_SPLIT poll_kernel<ExactF32, kWarps, 1, kTile32, kStages, true>
-#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 0, true>
-#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 1, true>
+#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 0, true>
+#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 1, true>
 constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
                           2 * kWarps * sizeof(WarpPartial<float>);
 
@@ -143,15 +147,15 @@ constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * siz
 typedef void (*Poll2Fn)(const PollArgs2<float>);
 static Poll2Fn fast_variant(int v) {
     switch (v) {
-        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2>;
-        case 1: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3>;
-        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 4>;
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(2)>;
+        case 1: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3)>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(4)>;
     }
 }
 static Poll2Fn verified_variant(int v) {
     switch (v) {
-        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 2, 1>;
-        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, 3, 1>;
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(2), 1>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 1>;
     }
 }
 

@@ -77,6 +77,7 @@ def _top_k(x, k):
 def _kb():
     kb = types.ModuleType('keras.backend')
     kb.floatx = lambda: FLOATX
+    kb.image_data_format = lambda: 'channels_last'
     kb.shape = lambda x: np.asarray(x).shape
     kb.abs = np.abs
     kb.greater = lambda a, b: np.greater(a, b)
