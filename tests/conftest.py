@@ -20,7 +20,7 @@ def load_planes(tag):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('detect_'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('detect_', 'driver_')))
 
 
 def load_golden(name):
