@@ -338,12 +338,14 @@ def main():
                'host_cpu_count': os.cpu_count()}
 
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, 'profiles', 'r01g_traffic_c4.json')
-    if args.mode == 'verified' and args.images == 4096 and args.planes == '22k' and os.path.exists(tpath):
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic_c4.json')))     # newest capture last
+    tpath = tfiles[-1] if tfiles else ''
+    if args.mode == 'verified' and args.images == 4096 and args.planes == '22k' and tpath:
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # bytes per launch, from the ncu capture
-        traffic_src = 'profiles/r01g_traffic_c4.json (ncu --set full capture of this launch)'
+        traffic_src = 'profiles/%s (ncu --set full capture of this launch)' % os.path.basename(tpath)
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         achieved = W_ALG * value / world / 1e12              # per-GPU TFLOP/s of algorithmic work
