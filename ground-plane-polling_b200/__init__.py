@@ -14,7 +14,8 @@ from .layers.fit_road_planes import (FitRoadPlanes, PlanePoller, fit_road_planes
 from .layers._misc import RegressBoxes, RegressDims, decode, decode_torch  # noqa: F401
 from .layers.filter_detections import (FilterDetections, filter_detections, filter_detections_batch,  # noqa: F401
                                        filter_detections_torch)
-from . import pipeline  # noqa: F401
+from . import pipeline, sharding  # noqa: F401
+from .sharding import fit_road_planes_multi, fit_road_planes_sharded, shard_bounds  # noqa: F401
 from .pipeline import detections_from_heads  # noqa: F401
 from .utils import synthetic  # noqa: F401
 from .utils import pose  # noqa: F401

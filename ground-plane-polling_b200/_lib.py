@@ -21,6 +21,7 @@ c_int = ctypes.c_int
 # name -> (restype, argtypes); mirrors include/gpp.h one to one (tests/test_capi.py checks the list)
 SIGNATURES = {
     'gpp_version': (c_int, []),
+    'gpp_device_count': (c_int, []),
     'gpp_last_error': (ctypes.c_char_p, []),
     'gpp_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     'gpp_destroy': (c_int, [c_void_p]),

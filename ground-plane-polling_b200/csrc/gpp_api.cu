@@ -95,6 +95,14 @@ extern "C" {
 
 int gpp_version(void) { return GPP_VERSION; }
 const char *gpp_last_error(void) { return g_last_error.c_str(); }
+int gpp_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();          // clear the sticky "no device" error
+        return 0;
+    }
+    return count;
+}
 
 int gpp_create(int device, gpp_handle **out) {
     if (!out) return set_error(GPP_EINVAL, "gpp_create: out is NULL");

@@ -1,12 +1,16 @@
 """
-Multi-GPU sharding of the polling path: one process per GPU, the image axis is split
-into contiguous shards, the plane database is replicated on every GPU, and there is NO collective on the
-data path -- every (image, detection) is independent.  ``torch.distributed`` only provides rank / world size
-and the optional result gather to rank 0.
+Multi-GPU sharding of the polling path: the image axis is split into contiguous shards, the
+plane database is replicated on every GPU, and there is NO collective on the data path -- every (image, detection)
+is independent.
+
+  fit_road_planes_sharded   one process per GPU (torchrun); ``torch.distributed`` only provides rank / world size and
+                            the optional result gather to rank 0
+  fit_road_planes_multi     one process, one host thread + one libgpp handle per GPU; results land in disjoint slices
+                            of one set of host arrays (the numpy drop-in for a multi-GPU box)
 """
 import numpy as np
 
-__all__ = ['shard_bounds', 'fit_road_planes_sharded']
+__all__ = ['shard_bounds', 'fit_road_planes_sharded', 'fit_road_planes_multi']
 
 
 def shard_bounds(n_images, world_size, rank):
@@ -50,3 +54,65 @@ def fit_road_planes_sharded(boxes, dimensions, orientations, P_inv, planes, mode
         return None
     gathered.sort(key=lambda t: t[0])
     return [np.concatenate([g[2][i] for g in gathered], axis=0) for i in range(len(outs))]
+
+
+def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, devices=None, mode=None, return_index=False,
+                          fit_fn=None):
+    """``fit_road_planes`` over several GPUs of one box from ONE process: device ``devices[i]`` polls the i-th
+    contiguous shard of images (its own handle, stream and copy of the database); one host thread per device drives
+    it (the C calls release the GIL) and writes straight into the shard's slice of the result arrays.
+
+    ``devices`` defaults to every visible GPU.  ``planes`` is one database shared by the batch ((N, 4) or (1, N, 4) or
+    a (B, N, 4) tile of one database).  ``fit_fn(boxes, dims, orient, P_inv, planes, mode=, return_index=, device=,
+    out=)`` defaults to ``gpp_b200.fit_road_planes`` (tests inject a stand-in to exercise the host logic on CPU).
+    """
+    import threading
+    if fit_fn is None:
+        from .layers.fit_road_planes import fit_road_planes as fit_fn
+    if devices is None:
+        from . import _lib
+        devices = list(range(_lib.load().gpp_device_count()))
+    devices = list(devices)
+    if not devices:
+        raise RuntimeError('fit_road_planes_multi: no CUDA device; libgpp has no CPU fallback')
+    boxes = np.asarray(boxes)
+    if boxes.ndim != 3:
+        raise ValueError('boxes must have shape (B, D, 12), got %r' % (boxes.shape,))
+    dimensions, orientations, P_inv = np.asarray(dimensions), np.asarray(orientations), np.asarray(P_inv)
+    planes = np.asarray(planes)
+    if planes.ndim == 3:
+        if planes.shape[0] != 1 and not all(np.array_equal(planes[0], planes[b]) for b in range(1, planes.shape[0])):
+            raise ValueError('fit_road_planes_multi takes one plane database shared by the batch')
+        planes = planes[0]
+    B, D = boxes.shape[:2]
+    out_t = np.float64 if mode == 'f64' else np.float32
+    out = [np.empty((B, D, 4, 3), out_t), np.empty((B, D, 1, 4), out_t), np.empty((B, D), out_t)]
+    if return_index:
+        out.append(np.empty((B, D), np.int64))
+    shards = [(dev,) + shard_bounds(B, len(devices), i) for i, dev in enumerate(devices)]
+    shards = [s for s in shards if s[2] > s[1]]
+
+    def run(shard):
+        dev, b0, b1 = shard
+        fit_fn(boxes[b0:b1], dimensions[b0:b1], orientations[b0:b1], P_inv[b0:b1], planes, mode=mode,
+               return_index=return_index, device=dev, out=[o[b0:b1] for o in out])
+
+    if len(shards) == 1:
+        run(shards[0])
+    elif shards:
+        errors = []
+
+        def guarded(shard):
+            try:
+                run(shard)
+            except BaseException as e:  # noqa: B902 -- re-raised in the caller's thread below
+                errors.append(e)
+
+        threads = [threading.Thread(target=guarded, args=(s,), name='gpp-dev%d' % s[0]) for s in shards]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+    return out

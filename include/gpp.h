@@ -53,6 +53,9 @@ typedef struct gpp_handle gpp_handle;
 
 int gpp_version(void);
 const char *gpp_last_error(void);
+/* Number of CUDA devices visible to the process (0 without a driver / GPU; never fails).  Multi-GPU callers create one
+ * handle per device and shard the images: the path has no cross-device step. */
+int gpp_device_count(void);
 
 /* Create / destroy a polling context on CUDA device `device` (>= 0). */
 int gpp_create(int device, gpp_handle **out);

@@ -242,3 +242,18 @@ def test_large_batch_properties_config4_slice(gpp):
     pick = np.random.default_rng(1).choice(B, size=6, replace=False)
     want = c_oracle.fit_road_planes_c(boxes[pick], dims[pick], orient[pick], P_inv[pick], planes, return_index=True)
     _assert_identical([h[pick] for h in host], want)
+
+
+def test_multi_device_driver_equals_single_device(gpp):
+    """fit_road_planes_multi over every visible GPU == fit_road_planes on one (bit for bit); with one GPU this
+    exercises the single-shard path, under `gpurun --gpus N` the threaded one."""
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(37, 100, planes, seed=91, n_valid=40)
+    n = gpp._lib.load().gpp_device_count()
+    assert n >= 1
+    want = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, return_index=True)
+    got = gpp.fit_road_planes_multi(boxes, dims, orient, P_inv, planes, return_index=True)
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
+    got = gpp.fit_road_planes_multi(boxes, dims, orient, P_inv, planes[None], devices=list(range(n))[::-1], mode='f64')
+    want = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64')
+    assert got[0].dtype == np.float64 and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
