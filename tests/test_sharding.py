@@ -93,14 +93,14 @@ def test_single_process_multi_device_driver_host_logic():
             assert dst.flags['C_CONTIGUOUS'] and dst.shape == src.shape
             dst[...] = src
         with lock:
-            calls.append((device, b.shape[0], threading.get_ident()))
+            calls.append((device, b.shape[0], threading.current_thread().name))
 
     got = fit_road_planes_multi(boxes, dims, orient, P_inv, np.tile(planes[None], (7, 1, 1)), devices=[4, 5, 6],
                                 return_index=True, fit_fn=fit_fn)
     want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, nthreads=1, return_index=True)
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
     assert sorted((c[0], c[1]) for c in calls) == [(4, 3), (5, 2), (6, 2)]
-    assert len({c[2] for c in calls}) == 3                        # one host thread per device
+    assert sorted(c[2] for c in calls) == ['gpp-dev4', 'gpp-dev5', 'gpp-dev6']      # one host thread per device
     # more devices than images: the empty shards are not dispatched
     calls.clear()
     got = fit_road_planes_multi(boxes[:2], dims[:2], orient[:2], P_inv[:2], planes, devices=[0, 1, 2, 3], fit_fn=fit_fn)
