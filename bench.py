@@ -319,6 +319,31 @@ def main():
                 oms.append(poller.last_kernel_ms())
         other_modes[other] = world * hyp_per_step / (max_over_ranks(float(np.mean(oms))) * 1e-3)
 
+    # ---------------- the smaller configurations of BASELINE.json, for context (N = 1 only; the bench line is C4)
+    other_workloads = None
+    if rank == 0 and world == 1:
+        other_workloads = {}
+        for tag, (img, db) in (('C3_64x100x10k', (64, '10k')), ('C2_1x100x1k', (1, '1k')), ('1x100x22k', (1, '22k'))):
+            pl = load_planes(db)
+            wb, wd, wo, wp = make_workload(img, args.dets, pl, seed=11)
+            poller.set_planes(pl)
+            tw = [torch.from_numpy(a).to(dev) for a in (wb, wd, wo, wp)]
+            kms, calls = [], []
+            for i in range(6):
+                poller.fit_torch(*tw, mode=args.mode)
+                torch.cuda.synchronize()
+                if i:
+                    kms.append(poller.last_kernel_ms())
+            for i in range(6):
+                c0 = time.time()
+                gpp_b200.fit_road_planes(wb, wd, wo, wp, pl, mode=args.mode, device=local_rank)
+                if i:
+                    calls.append(time.time() - c0)
+            hyp = float(img) * args.dets * pl.shape[0]
+            other_workloads[tag] = {'kernel_ms': float(np.mean(kms)), 'hyp_per_s_kernel': hyp / (np.mean(kms) * 1e-3),
+                                    'numpy_call_ms': 1e3 * float(np.mean(calls))}
+        poller.set_planes(planes)
+
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,6 +393,7 @@ def main():
                          'kernel_ms_per_launch': ms_per_step},
             'cpu_baseline': cpu,
             'other_modes': dict(other_modes, unit=UNIT),
+            'other_workloads': other_workloads,
             'wall_ms_per_step_device_leg': 1e3 * wall_dev / args.steps,
             'kernel_ms_steps': [round(x, 3) for x in kernel_ms],
         }

@@ -175,10 +175,13 @@ int configure_kernels(gpp_handle *h) {
     return GPP_OK;
 }
 
-// small batches: fewer detections than a few per resident CTA -> one detection per CTA, planes split over warps
-static bool use_split(const gpp_handle *h, long long n_det) {
+// Small batches: one detection per CTA, planes split over the warps (kSplit kernels).  The batch kernels need
+// several groups of eight detections per resident CTA to fill the GPU; measured crossover on B200
+// (scripts/gpu_small_batches.py, 100-detection images x 10k / 22k planes): ~50 images for VERIFIED, ~40 for FAST,
+// ~22 for EXACT, i.e. about `per_sm` detections per SM.
+static bool use_split(const gpp_handle *h, long long n_det, int per_sm) {
     if (h->force_split) return h->force_split > 0;
-    return n_det < 4LL * h->sm_count * 3;
+    return n_det < (long long)per_sm * h->sm_count;
 }
 
 // All work-list slots are (re)allocated together, so that a steady stream of calls never hits cudaMalloc (which
@@ -328,7 +331,7 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
         b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
         b.det_list = a.det_list; b.det_count = a.det_count;
         b.group_counter = w->count + 2;
-        const bool split = use_split(h, a.n_det);
+        const bool split = use_split(h, a.n_det, mode == GPP_MODE_VERIFIED ? 33 : 27);
         const long long n_groups = split ? a.n_det : (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
@@ -358,7 +361,7 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
             if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
             fast_variant(v)<<<(unsigned)grid_for(h, n_groups, h->occ2[v]), kWarps * 32, kSmem2, s>>>(b);
         }
-    } else if (use_split(h, a.n_det)) {
+    } else if (use_split(h, a.n_det, 15)) {
         GPP_K_EXACT_SPLIT<<<(unsigned)grid_for(h, a.n_det, h->occ_split[0]), kWarps * 32, kSmem1, s>>>(a);
     } else {
         // two detections per warp once every SM has several groups to chew on
@@ -382,7 +385,7 @@ int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a_in, cudaStream_t s)
     if (rc) return rc;
     PollArgs<double> a = a_in;
     a.det_list = w->ulist; a.det_count = w->count + 1;
-    if (use_split(h, a.n_det)) {
+    if (use_split(h, a.n_det, 12)) {
         GPP_K_F64_SPLIT<<<(unsigned)grid_for(h, a.n_det, h->occ_split[3]), kWarps * 32, kSmem64, s>>>(a);
     } else {
         const long long n_groups = (a.n_det + kWarps - 1) / kWarps;

@@ -110,11 +110,7 @@ struct PackFast {
     typedef FastF32 Scalar;
     static __device__ __forceinline__ f2 madd(f2 a, f2 b, f2 c) { return fma2(a, b, c); }
     static __device__ __forceinline__ f2 rcp(f2 a) { return pk(rcp_approx(lo(a)), rcp_approx(hi(a))); }
-#ifdef GPP_EXP_NOSQRT   /* timing experiment only: wrong results */
-    static __device__ __forceinline__ f2 sqrt(f2 a) { return a; }
-#else
     static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(sqrt_approx(lo(a)), sqrt_approx(hi(a))); }
-#endif
 };
 
 // Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
