@@ -167,6 +167,7 @@ int gpp_destroy(gpp_handle *h) {
     }
     for (int i = 0; i < gpp_handle::kStreams; ++i) {
         h->stage[i].release();
+        h->hstage[i].release();
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     }
     for (auto &p : h->chunk_events) {
@@ -355,6 +356,32 @@ void gpp::Staging::release() {
     cap_det = 0; cap_img = 0; out_elem = 0;
 }
 
+int gpp::HostStaging::reserve(size_t bytes) {
+    if (!done) GPP_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    if (bytes <= cap) return GPP_OK;
+    if (base) cudaFreeHost(base);
+    base = nullptr; cap = 0;
+    GPP_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&base), bytes, cudaHostAllocDefault));
+    cap = bytes;
+    return GPP_OK;
+}
+
+void gpp::HostStaging::release() {
+    if (base) cudaFreeHost(base);
+    if (done) cudaEventDestroy(done);
+    base = nullptr; cap = 0; done = nullptr;
+}
+
+// true iff `p` is ordinary (pageable) host memory, i.e. neither cudaHostAlloc'ed / registered nor managed
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
 template <class T>
 static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, const int32_t *orient,
                          const float *pinv, int B, int D, T *keypoints, T *keyplanes, T *residuals,
@@ -379,16 +406,61 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         GPP_CUDA(cudaEventCreate(&b));
         h->chunk_events.push_back(std::make_pair(a, b));
     }
+    // Pageable caller memory and more than one chunk: go through the pinned staging blocks (see HostStaging)
+    const bool staged = n_chunks > 1 && (is_pageable(boxes) || is_pageable(dims) || is_pageable(orient) ||
+                                         is_pageable(pinv) || is_pageable(keypoints) || is_pageable(keyplanes) ||
+                                         is_pageable(residuals) || (best && is_pageable(best)));
+    const size_t cd = (size_t)imgs_per_chunk * D, ci = (size_t)imgs_per_chunk;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_boxes = 0, o_dims = o_boxes + up(48 * cd), o_orient = o_dims + up(12 * cd),
+                 o_pinv = o_orient + up(4 * cd), o_kp = o_pinv + up(48 * ci), o_kpl = o_kp + up(sizeof(T) * 12 * cd),
+                 o_res = o_kpl + up(sizeof(T) * 4 * cd), o_best = o_res + up(sizeof(T) * cd),
+                 o_end = o_best + up(8 * cd);
+    if (staged)
+        for (int i = 0; i < n_streams; ++i) {
+            int rc = h->hstage[i].reserve(o_end);
+            if (rc) return rc;
+        }
+    // copies the finished outputs of chunk c from its pinned block to the caller's arrays
+    auto drain = [&](int c) -> int {
+        const int b0 = c * imgs_per_chunk;
+        const int nb = (b0 + imgs_per_chunk <= B) ? imgs_per_chunk : (B - b0);
+        const size_t m0 = (size_t)b0 * D, nm = (size_t)nb * D;
+        gpp::HostStaging &hs = h->hstage[c % n_streams];
+        GPP_CUDA(cudaEventSynchronize(hs.done));
+        memcpy(keypoints + 12 * m0, hs.base + o_kp, sizeof(T) * 12 * nm);
+        memcpy(keyplanes + 4 * m0, hs.base + o_kpl, sizeof(T) * 4 * nm);
+        memcpy(residuals + m0, hs.base + o_res, sizeof(T) * nm);
+        if (best) memcpy(best + m0, hs.base + o_best, sizeof(long long) * nm);
+        return GPP_OK;
+    };
     for (int c = 0; c < n_chunks; ++c) {
         const int b0 = c * imgs_per_chunk;
         const int nb = (b0 + imgs_per_chunk <= B) ? imgs_per_chunk : (B - b0);
         const long long m0 = (long long)b0 * D, nm = (long long)nb * D;
         gpp::Staging &st = h->stage[c % n_streams];
+        gpp::HostStaging &hs = h->hstage[c % n_streams];
         cudaStream_t s = h->streams[c % n_streams];
-        GPP_CUDA(cudaMemcpyAsync(st.boxes, boxes + 12 * m0, sizeof(float) * 12 * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.dims, dims + 3 * m0, sizeof(float) * 3 * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.orient, orient + m0, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.pinv, pinv + 12 * (size_t)b0, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
+        const float *src_boxes = boxes + 12 * m0, *src_dims = dims + 3 * m0, *src_pinv = pinv + 12 * (size_t)b0;
+        const int32_t *src_orient = orient + m0;
+        if (staged) {
+            if (c >= n_streams) {                     // the block's previous chunk: outputs out, inputs long consumed
+                int rc = drain(c - n_streams);
+                if (rc) return rc;
+            }
+            memcpy(hs.base + o_boxes, src_boxes, sizeof(float) * 12 * nm);
+            memcpy(hs.base + o_dims, src_dims, sizeof(float) * 3 * nm);
+            memcpy(hs.base + o_orient, src_orient, sizeof(int32_t) * nm);
+            memcpy(hs.base + o_pinv, src_pinv, sizeof(float) * 12 * nb);
+            src_boxes = reinterpret_cast<const float *>(hs.base + o_boxes);
+            src_dims = reinterpret_cast<const float *>(hs.base + o_dims);
+            src_orient = reinterpret_cast<const int32_t *>(hs.base + o_orient);
+            src_pinv = reinterpret_cast<const float *>(hs.base + o_pinv);
+        }
+        GPP_CUDA(cudaMemcpyAsync(st.boxes, src_boxes, sizeof(float) * 12 * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.dims, src_dims, sizeof(float) * 3 * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.orient, src_orient, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
+        GPP_CUDA(cudaMemcpyAsync(st.pinv, src_pinv, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
         gpp::PollArgs<T> a;
         a.boxes = st.boxes; a.dims = st.dims; a.orient = st.orient; a.pinv = st.pinv;
         a.planes = f64 ? (const void *)h->d_planes64 : (const void *)h->d_planes32;
@@ -402,12 +474,23 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         int rc = gpp::launch_poll(h, a, mode, s);
         if (rc) return rc;
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].second, s));
-        GPP_CUDA(cudaMemcpyAsync(keypoints + 12 * m0, st.keypoints, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
-        GPP_CUDA(cudaMemcpyAsync(keyplanes + 4 * m0, st.keyplanes, sizeof(T) * 4 * nm, cudaMemcpyDeviceToHost, s));
-        GPP_CUDA(cudaMemcpyAsync(residuals + m0, st.residuals, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
-        if (best)
-            GPP_CUDA(cudaMemcpyAsync(best + m0, st.best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
+        T *dst_kp = staged ? reinterpret_cast<T *>(hs.base + o_kp) : keypoints + 12 * m0;
+        T *dst_kpl = staged ? reinterpret_cast<T *>(hs.base + o_kpl) : keyplanes + 4 * m0;
+        T *dst_res = staged ? reinterpret_cast<T *>(hs.base + o_res) : residuals + m0;
+        GPP_CUDA(cudaMemcpyAsync(dst_kp, st.keypoints, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
+        GPP_CUDA(cudaMemcpyAsync(dst_kpl, st.keyplanes, sizeof(T) * 4 * nm, cudaMemcpyDeviceToHost, s));
+        GPP_CUDA(cudaMemcpyAsync(dst_res, st.residuals, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
+        if (best) {
+            int64_t *dst_best = staged ? reinterpret_cast<int64_t *>(hs.base + o_best) : best + m0;
+            GPP_CUDA(cudaMemcpyAsync(dst_best, st.best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
+        }
+        if (staged) GPP_CUDA(cudaEventRecord(hs.done, s));
     }
+    if (staged)
+        for (int c = (n_chunks > n_streams ? n_chunks - n_streams : 0); c < n_chunks; ++c) {
+            int rc = drain(c);
+            if (rc) return rc;
+        }
     for (int i = 0; i < n_streams; ++i) GPP_CUDA(cudaStreamSynchronize(h->streams[i]));
     h->timing_chunks = n_chunks;
     h->timing_single = false;

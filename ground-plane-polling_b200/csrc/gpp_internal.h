@@ -26,6 +26,17 @@ struct Staging {
     void release();
 };
 
+// Pinned host staging of one chunk (inputs and outputs) for callers that pass pageable memory: an asynchronous copy
+// to or from pageable memory blocks the host until it is done, which serialises the chunks of a large call; with
+// the staging block the host only does plain memcpy while the GPU works on the other chunk.
+struct HostStaging {
+    unsigned char *base = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;      // recorded after the chunk's last device-to-host copy
+    int reserve(size_t bytes);
+    void release();
+};
+
 }  // namespace gpp
 
 struct gpp_handle {
@@ -58,6 +69,7 @@ struct gpp_handle {
     // host-entry plumbing
     cudaStream_t streams[kStreams] = {nullptr, nullptr};
     gpp::Staging stage[kStreams];
+    gpp::HostStaging hstage[kStreams];       // pinned, only allocated when a caller passes pageable memory
     std::vector<std::pair<cudaEvent_t, cudaEvent_t> > chunk_events;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     int timing_chunks = 0;

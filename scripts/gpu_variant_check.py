@@ -1,4 +1,4 @@
-"""Development aid: a VERIFIED kernel variant (debug_set_config code, default 4 = barrier-free + deferral) against
+"""Development aid: a VERIFIED kernel variant (debug_set_config code, 2 = 2 CTAs per SM, 3 = 3 CTAs per SM) against
 EXACT, bit for bit, then its timing against the default variant."""
 import os, sys
 import numpy as np
@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch
 import gpp_b200
 from gpp_b200.utils import synthetic
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 poller = gpp_b200.get_poller(0)
 dev = torch.device('cuda', 0)
 bad = 0

@@ -257,3 +257,31 @@ def test_multi_device_driver_equals_single_device(gpp):
     got = gpp.fit_road_planes_multi(boxes, dims, orient, P_inv, planes[None], devices=list(range(n))[::-1], mode='f64')
     want = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64')
     assert got[0].dtype == np.float64 and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
+
+
+def test_chunked_host_path_pageable_and_pinned_memory(gpp):
+    """Calls with more than 65536 detections are pipelined in chunks; pageable caller memory goes through pinned
+    staging blocks, pinned caller memory is copied directly.  Both equal the oracle, with and without the index,
+    with a ragged last chunk, and in the FP64 mode."""
+    import torch
+    planes = load_planes('100')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(1501, 100, planes, seed=5, n_valid=70)
+    P32 = P_inv.astype(np.float32)
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P32, planes, return_index=True)
+    got = gpp.fit_road_planes(boxes, dims, orient, P32, planes, mode='exact', return_index=True)        # pageable
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
+    got = gpp.fit_road_planes(boxes, dims, orient, P32, planes, mode='verified')
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want[:3]))
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    keep = [pinned(a) for a in (boxes, dims, orient, P32)]
+    outs = [torch.empty(w.shape, dtype=torch.from_numpy(w).dtype, pin_memory=True) for w in want]
+    res = gpp.fit_road_planes(*[t.numpy() for t in keep], planes, mode='verified', return_index=True,
+                              out=[t.numpy() for t in outs])
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(res, want))
+    w64 = c_oracle.fit_road_planes_c(boxes[:700], dims[:700], orient[:700], P32[:700], planes, dtype=np.float64)
+    g64 = gpp.fit_road_planes(boxes[:700], dims[:700], orient[:700], P32[:700], planes, mode='f64')
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(g64, w64))
