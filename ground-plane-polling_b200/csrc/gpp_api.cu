@@ -394,7 +394,11 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
     int imgs_per_chunk = (int)(max_chunk_det / (D > 0 ? D : 1));
     if (imgs_per_chunk < 1) imgs_per_chunk = 1;
     if (imgs_per_chunk > B) imgs_per_chunk = B;
-    const int n_chunks = (B + imgs_per_chunk - 1) / imgs_per_chunk;
+    // chunk boundaries (in images); uniform chunks (small first / last chunks were measured: the less efficient
+    // small launches cost more than the shorter exposed copies save)
+    std::vector<int> start(1, 0);
+    while (start.back() < B) start.push_back(start.back() + imgs_per_chunk < B ? start.back() + imgs_per_chunk : B);
+    const int n_chunks = (int)start.size() - 1;
     const int n_streams = n_chunks > 1 ? gpp_handle::kStreams : 1;
     for (int i = 0; i < n_streams; ++i) {
         int rc = h->stage[i].reserve((long long)imgs_per_chunk * D, imgs_per_chunk, f64);
@@ -423,8 +427,7 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         }
     // copies the finished outputs of chunk c from its pinned block to the caller's arrays
     auto drain = [&](int c) -> int {
-        const int b0 = c * imgs_per_chunk;
-        const int nb = (b0 + imgs_per_chunk <= B) ? imgs_per_chunk : (B - b0);
+        const int b0 = start[c], nb = start[c + 1] - start[c];
         const size_t m0 = (size_t)b0 * D, nm = (size_t)nb * D;
         gpp::HostStaging &hs = h->hstage[c % n_streams];
         GPP_CUDA(cudaEventSynchronize(hs.done));
@@ -435,8 +438,7 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         return GPP_OK;
     };
     for (int c = 0; c < n_chunks; ++c) {
-        const int b0 = c * imgs_per_chunk;
-        const int nb = (b0 + imgs_per_chunk <= B) ? imgs_per_chunk : (B - b0);
+        const int b0 = start[c], nb = start[c + 1] - start[c];
         const long long m0 = (long long)b0 * D, nm = (long long)nb * D;
         gpp::Staging &st = h->stage[c % n_streams];
         gpp::HostStaging &hs = h->hstage[c % n_streams];
