@@ -267,7 +267,7 @@ def _plane_groups(planes, B):
 
 
 def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False, device=None,
-                    out=None):
+                    out=None, return_pose=False):
     """ Identify 3D keypoints and keyplane for each detection (drop-in for fit_road_planes.py:49).
     Args
         boxes                 : (num_batch, num_dets, 12) boxes in (x1, y1, x2, y2, xl, yl, xm, ym, xr, yr, xt, yt) format.
@@ -282,8 +282,18 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
         residuals is shaped (num_batch, num_dets) and contains the best 'error of fit' corresponding to the keyplane.
     Extensions (do not change the default return list): ``mode`` 'verified' | 'exact' | 'fast' | 'f64',
     ``return_index`` appends the winning plane index (int64), ``device`` picks the GPU, ``out`` is a list of
-    preallocated result arrays (single shared database only).
+    preallocated result arrays (single shared database only), ``return_pose`` appends ``locations (B, D, 3)``,
+    ``angles (B, D, 3)`` (Rodrigues vector) and the corrected ``dimensions (B, D, 3)`` of EVERY row as the driver
+    computes them for the rows it keeps (bin/run_network.py:137-247, ``recover_pose``).
     """
+    if return_pose:
+        res = fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=mode, return_index=return_index,
+                              device=device, out=out)
+        from ..utils.pose import recover_pose
+        shape = res[2].shape
+        loc, ang, dim = recover_pose(res[0].reshape(-1, 12), np.asarray(dimensions).reshape(-1, 3),
+                                     np.asarray(orientations).reshape(-1), device=device)
+        return list(res) + [loc.reshape(shape + (3,)), ang.reshape(shape + (3,)), dim.reshape(shape + (3,))]
     poller = get_poller(device)
     boxes = np.asarray(boxes)
     if boxes.ndim != 3:
@@ -304,10 +314,19 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     return [np.concatenate([p[i] for p in parts], axis=0) for i in range(len(parts[0]))]
 
 
-def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False):
+def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False,
+                          return_pose=False):
     """Same operator on CUDA tensors (zero-copy, torch's current stream, no host sync).  ``planes`` is one
-    (N, 4) / (1, N, 4) database shared by the batch (torch tensor on any device, or numpy)."""
+    (N, 4) / (1, N, 4) database shared by the batch (torch tensor on any device, or numpy).  ``return_pose`` appends
+    locations, angles and corrected dimensions, (B, D, 3) each, computed on the device right behind the polling."""
     import torch
+    if return_pose:
+        res = fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=mode,
+                                    return_index=return_index)
+        from ..utils.pose import recover_pose_torch
+        shape = tuple(res[2].shape)
+        loc, ang, dim = recover_pose_torch(res[0].to(torch.float32), dimensions, orientations)
+        return list(res) + [loc.view(shape + (3,)), ang.view(shape + (3,)), dim.view(shape + (3,))]
     poller = get_poller(boxes.device.index if boxes.device.index is not None else torch.cuda.current_device())
     if isinstance(planes, torch.Tensor):
         if planes.dim() == 3:

@@ -90,3 +90,27 @@ def test_postprocess_image_mirrors_the_driver(gpp):
     lines = gpp.kitti.format_kitti_lines(out['boxes'], out['dimensions'], out['locations'], out['scores'],
                                          out['kitti'], (1242, 375))
     assert len(lines) == len(keep) and lines[0].startswith('Car -1 -1 ')
+
+
+def test_return_pose_extension(gpp):
+    """fit_road_planes(..., return_pose=True) appends what recover_pose gives for every row; the default return list
+    is unchanged; numpy and torch entries agree bit for bit."""
+    import torch
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 40, planes, seed=93, n_valid=31)
+    base = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes)
+    assert len(base) == 3
+    full = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, return_index=True, return_pose=True)
+    assert len(full) == 7 and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(full[:3], base))
+    loc, ang, dout = gpp.recover_pose(base[0].reshape(-1, 12), dims.reshape(-1, 3), orient.reshape(-1))
+    assert full[4].shape == full[5].shape == full[6].shape == (3, 40, 3)
+    assert np.array_equal(full[4].reshape(-1, 3), loc, equal_nan=True)
+    assert np.array_equal(full[5].reshape(-1, 3), ang, equal_nan=True)
+    assert np.array_equal(full[6].reshape(-1, 3), dout, equal_nan=True)
+    dev = torch.device('cuda', 0)
+    t = gpp.fit_road_planes_torch(torch.from_numpy(boxes).to(dev), torch.from_numpy(dims).to(dev),
+                                  torch.from_numpy(orient).to(dev), torch.from_numpy(P_inv.astype(np.float32)).to(dev),
+                                  planes, return_pose=True)
+    assert len(t) == 6
+    for a, b in zip(t[3:], full[4:]):
+        assert np.array_equal(a.cpu().numpy(), b, equal_nan=True)
