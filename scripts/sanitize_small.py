@@ -24,4 +24,29 @@ kp = got[0].astype(np.float32).reshape(-1, 12)
 loc, ang, dd = gpp_b200.recover_pose(kp, dims.reshape(-1, 3), orient.reshape(-1))
 gpp_b200.kitti_records(loc, ang, dd)
 poller.debug_scores(boxes[0, 0], dims[0, 0], orient[0, 0], P_inv[0], which=2, with_margin=True)
-print('sanitize_small: all paths ran, exact/verified == oracle')
+# the steps before polling and the device pipeline (decode, FilterDetections, heads -> polled detections)
+import torch
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+from gpp_b200.utils.anchors import anchors_for_shape
+from oracle import detect_ref
+rng = np.random.default_rng(3)
+anchors = anchors_for_shape((96, 160)).astype(np.float32)
+A = anchors.shape[0]
+reg = rng.normal(0, 1, (2, A, 12)).astype(np.float32)
+rdim = rng.normal(0, 1, (2, A, 3)).astype(np.float32)
+cls = (rng.random((2, A, 8)) ** 6).astype(np.float32)
+b_, d_ = gpp_b200.decode(anchors, reg, cls, rdim)
+wb, wd = detect_ref.decode_ref(anchors, reg, cls, rdim)
+assert np.array_equal(b_, wb) and np.array_equal(d_, wd)
+got = gpp_b200.filter_detections_batch(b_, d_, cls)
+want = detect_ref.filter_detections_ref(b_, d_, cls)
+assert all(np.array_equal(g, w) for g, w in zip(got, want))
+dev = torch.device('cuda', 0)
+outs = gpp_b200.detections_from_heads(*[torch.from_numpy(a).to(dev) for a in (anchors, reg, rdim, cls)],
+                                      torch.from_numpy(P_inv[:2].astype(np.float32)).to(dev), planes)
+torch.cuda.synchronize()
+assert outs[5].shape == (2, 100, 4, 3)
+# chunked host path through the pinned staging blocks (pageable memory, > 65536 detections)
+big = synthetic.synth_detections(700, 100, planes[:64], seed=9)
+gpp_b200.fit_road_planes(*big, planes[:64], mode='verified', return_index=True)
+print('sanitize_small: all paths ran, exact/verified/decode/filter == oracle')
