@@ -185,73 +185,101 @@ __device__ __forceinline__ f2 dot3p(f2 a0, f2 a1, f2 a2, float b0, float b1, flo
 //      |X_l - X_t|^2 = |a|^2 + q (2 a.n + q),  a = X_l - X_m,  a.n = |d| (sign(t_l) - sign(t_m))   (same for X_r)
 //    and a.n = 0 unless the plane separates the rays, which is tested once per warp.
 // About 55 FMA-pipe results, 8-9 MUFU and ~6 ALU-pipe instructions per hypothesis (direct formulation: 92 / 10 / 17).
-// kMargin: 0 = none, 1 = out.m = geometric margin + mc, 2 = geometric margin only (the caller accounts for mc)
-template <bool kMergedRcp, int kMargin, bool kLazyZ = false>
-__device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
-    const f2 t0 = fma2(n0, bc(D.fl[0]), fma2(n1, bc(D.fl[1]), n2));
-    const f2 t1 = fma2(n0, bc(D.fm[0]), fma2(n1, bc(D.fm[1]), n2));
-    const f2 t2 = fma2(n0, bc(D.fr[0]), fma2(n1, bc(D.fr[1]), n2));
-    const f2 u = fma2(n0, bc(D.ft[0]), fma2(n1, bc(D.ft[1]), n2));
-    const f2 den = fma2(neg2(u), u, bc(D.T));
-    const f2 ad = abs2(d4);
+// The evaluation comes in two stages so that the VERIFIED all-six phase can stop after the first one:
+//   eval_bottom: the three points on the plane and the squared lengths of the bottom-face edges / diagonal
+//                (residuals 1, 2, 3) -- nothing that involves X_t;
+//   eval_top   : X_t (u, perp.n, q) and the squared lengths of the two slanted edges (residuals 0, 4, 5), the
+//                error margin and z_dir_check.
+// eval_pair_fast = both stages + the square roots; every user of the fast arithmetic goes through these two.
+struct Bottom {
+    f2 t0, t1, t2;     // n . d_k for the rescaled rays (l, m, r)
+    f2 ad;             // |d|
+    f2 s1;             // depth scale of X_m
+    f2 w;              // margin weight |d| / t_min^2 (kMargin only)
+    f2 a[3], b[3];     // X_l - X_m, X_r - X_m
+    f2 na, nb, nc;     // |X_l - X_m|^2, |X_r - X_m|^2, |X_l - X_r|^2
+};
+
+template <bool kMergedRcp, bool kMargin>
+__device__ __forceinline__ void eval_bottom(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, Bottom &g) {
+    g.t0 = fma2(n0, bc(D.fl[0]), fma2(n1, bc(D.fl[1]), n2));
+    g.t1 = fma2(n0, bc(D.fm[0]), fma2(n1, bc(D.fm[1]), n2));
+    g.t2 = fma2(n0, bc(D.fr[0]), fma2(n1, bc(D.fr[1]), n2));
+    g.ad = abs2(d4);
     f2 i0, i1;
     if (kMergedRcp) {
         // 1/t_l and 1/t_m from one MUFU.RCP.  Only used once max-votes is known to be 6, where a degenerate
         // (inf/NaN) hypothesis can neither win nor change max-votes.
-        const f2 inv = PackFast::rcp(mul2(t0, t1));
-        i0 = mul2(inv, t1);
-        i1 = mul2(inv, t0);
+        const f2 inv = PackFast::rcp(mul2(g.t0, g.t1));
+        i0 = mul2(inv, g.t1);
+        i1 = mul2(inv, g.t0);
     } else {
-        i0 = PackFast::rcp(t0);
-        i1 = PackFast::rcp(t1);
+        i0 = PackFast::rcp(g.t0);
+        i1 = PackFast::rcp(g.t1);
     }
-    const f2 s0 = mul2(ad, abs2(i0));
-    const f2 s1 = mul2(ad, abs2(i1));
-    const f2 i2 = PackFast::rcp(abs2(t2));
-    const f2 s2 = mul2(ad, i2);
-    const f2 iden = PackFast::rcp(den);
+    const f2 s0 = mul2(g.ad, abs2(i0));
+    g.s1 = mul2(g.ad, abs2(i1));
+    const f2 i2 = PackFast::rcp(abs2(g.t2));
+    const f2 s2 = mul2(g.ad, i2);
     if (kMargin) {
         const f2 imax = pk(max3f(fabsf(lo(i0)), fabsf(lo(i1)), lo(i2)), max3f(fabsf(hi(i0)), fabsf(hi(i1)), hi(i2)));
-        const f2 w = mul2(mul2(imax, imax), ad);                         // |d| / t_min^2
-        const f2 g = fma2(abs2(iden), bc(D.msT), bc(D.ms));             // K u |d_k|^2 (1 + T/|perp.n|)
-        out.m = kMargin == 1 ? fma2(w, g, bc(D.mc)) : mul2(w, g);
+        g.w = mul2(mul2(imax, imax), g.ad);                              // |d| / t_min^2
     }
-    f2 a[3], b[3];
-    {
-        const f2 nx = neg2(mul2(bc(D.fm[0]), s1)), ny = neg2(mul2(bc(D.fm[1]), s1));      // -X_m (x, y)
-        a[0] = fma2(bc(D.fl[0]), s0, nx); a[1] = fma2(bc(D.fl[1]), s0, ny); a[2] = sub2(s0, s1);   // X_l - X_m
-        b[0] = fma2(bc(D.fr[0]), s2, nx); b[1] = fma2(bc(D.fr[1]), s2, ny); b[2] = sub2(s2, s1);   // X_r - X_m
-    }
-    if (kLazyZ) {           // z_dir_check is only formed for the few pairs that get that far (see the callers)
-        out.za0 = a[0]; out.za2 = a[2]; out.zb0 = b[0]; out.zb2 = b[2];
-    } else {
-        out.zc = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
-    }
-    const f2 q = mul2(mul2(s1, fma2(u, bc(-D.G), mul2(t1, bc(D.T)))), iden);
+    const f2 nx = neg2(mul2(bc(D.fm[0]), g.s1)), ny = neg2(mul2(bc(D.fm[1]), g.s1));      // -X_m (x, y)
+    g.a[0] = fma2(bc(D.fl[0]), s0, nx); g.a[1] = fma2(bc(D.fl[1]), s0, ny); g.a[2] = sub2(s0, g.s1);   // X_l - X_m
+    g.b[0] = fma2(bc(D.fr[0]), s2, nx); g.b[1] = fma2(bc(D.fr[1]), s2, ny); g.b[2] = sub2(s2, g.s1);   // X_r - X_m
 #define GPP_SQN(v) fma2(v[2], v[2], fma2(v[1], v[1], mul2(v[0], v[0])))
-    const f2 na = GPP_SQN(a), nb = GPP_SQN(b);
+    g.na = GPP_SQN(g.a);
+    g.nb = GPP_SQN(g.b);
 #undef GPP_SQN
     // |X_l - X_r|^2 from the difference itself (|a|^2 + |b|^2 - 2 a.b would cancel when X_l is close to X_r)
-    const f2 c0 = sub2(a[0], b[0]), c1 = sub2(a[1], b[1]), c2 = sub2(a[2], b[2]);
-    const f2 nc = fma2(c2, c2, fma2(c1, c1, mul2(c0, c0)));
-    // does the plane separate the rays (sign(t_l) or sign(t_r) != sign(t_m)) for any pair of this warp?
-    const unsigned sd = ((__float_as_uint(lo(t0)) ^ __float_as_uint(lo(t1))) | (__float_as_uint(lo(t2)) ^ __float_as_uint(lo(t1))) |
-                         (__float_as_uint(hi(t0)) ^ __float_as_uint(hi(t1))) | (__float_as_uint(hi(t2)) ^ __float_as_uint(hi(t1)))) >> 31;
-    f2 ne, nf;
-    if (__any_sync(0xffffffffu, sd != 0u)) {
-        const f2 cs0 = pk(copysignf(lo(d4), lo(t0)), copysignf(hi(d4), hi(t0)));
-        const f2 cs1 = pk(copysignf(lo(d4), lo(t1)), copysignf(hi(d4), hi(t1)));
-        const f2 cs2 = pk(copysignf(lo(d4), lo(t2)), copysignf(hi(d4), hi(t2)));
-        ne = fma2(q, fma2(sub2(cs0, cs1), bc(2.0f), q), na);             // |X_l - X_t|^2
-        nf = fma2(q, fma2(sub2(cs2, cs1), bc(2.0f), q), nb);             // |X_r - X_t|^2
+    const f2 c0 = sub2(g.a[0], g.b[0]), c1 = sub2(g.a[1], g.b[1]), c2 = sub2(g.a[2], g.b[2]);
+    g.nc = fma2(c2, c2, fma2(c1, c1, mul2(c0, c0)));
+}
+
+// kMargin: 0 = none, 1 = out.m = geometric margin + mc, 2 = geometric margin only (the caller accounts for mc).
+// Sets out.r[0] (signed residual of the height) and leaves the SQUARED lengths of the slanted edges in ne / nf.
+template <int kMargin, bool kLazyZ>
+__device__ __forceinline__ void eval_top(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, const Bottom &g,
+                                         PairResult &out, f2 &ne, f2 &nf) {
+    const f2 u = fma2(n0, bc(D.ft[0]), fma2(n1, bc(D.ft[1]), n2));
+    const f2 den = fma2(neg2(u), u, bc(D.T));
+    const f2 iden = PackFast::rcp(den);
+    if (kMargin) {
+        const f2 f = fma2(abs2(iden), bc(D.msT), bc(D.ms));             // K u |d_k|^2 (1 + T/|perp.n|)
+        out.m = kMargin == 1 ? fma2(g.w, f, bc(D.mc)) : mul2(g.w, f);
+    }
+    if (kLazyZ) {           // z_dir_check is only formed for the few pairs that get that far (see the callers)
+        out.za0 = g.a[0]; out.za2 = g.a[2]; out.zb0 = g.b[0]; out.zb2 = g.b[2];
     } else {
-        ne = fma2(q, q, na);
-        nf = fma2(q, q, nb);
+        out.zc = fma2(g.a[2], g.b[0], neg2(mul2(g.a[0], g.b[2])));
+    }
+    const f2 q = mul2(mul2(g.s1, fma2(u, bc(-D.G), mul2(g.t1, bc(D.T)))), iden);
+    // does the plane separate the rays (sign(t_l) or sign(t_r) != sign(t_m)) for any pair of this warp?
+    const unsigned sd = ((__float_as_uint(lo(g.t0)) ^ __float_as_uint(lo(g.t1))) | (__float_as_uint(lo(g.t2)) ^ __float_as_uint(lo(g.t1))) |
+                         (__float_as_uint(hi(g.t0)) ^ __float_as_uint(hi(g.t1))) | (__float_as_uint(hi(g.t2)) ^ __float_as_uint(hi(g.t1)))) >> 31;
+    if (__any_sync(0xffffffffu, sd != 0u)) {
+        const f2 cs0 = pk(copysignf(lo(d4), lo(g.t0)), copysignf(hi(d4), hi(g.t0)));
+        const f2 cs1 = pk(copysignf(lo(d4), lo(g.t1)), copysignf(hi(d4), hi(g.t1)));
+        const f2 cs2 = pk(copysignf(lo(d4), lo(g.t2)), copysignf(hi(d4), hi(g.t2)));
+        ne = fma2(q, fma2(sub2(cs0, cs1), bc(2.0f), q), g.na);           // |X_l - X_t|^2
+        nf = fma2(q, fma2(sub2(cs2, cs1), bc(2.0f), q), g.nb);           // |X_r - X_t|^2
+    } else {
+        ne = fma2(q, q, g.na);
+        nf = fma2(q, q, g.nb);
     }
     out.r[0] = sub2(abs2(q), bc(D.td[0]));
-    out.r[1] = sub2(PackFast::sqrt(na), bc(D.td[1]));
-    out.r[2] = sub2(PackFast::sqrt(nb), bc(D.td[2]));
-    out.r[3] = sub2(PackFast::sqrt(nc), bc(D.td[3]));
+}
+
+template <bool kMergedRcp, int kMargin, bool kLazyZ = false>
+__device__ __forceinline__ void eval_pair_fast(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, PairResult &out) {
+    Bottom g;
+    eval_bottom<kMergedRcp, kMargin != 0>(D, n0, n1, n2, d4, g);
+    f2 ne, nf;
+    eval_top<kMargin, kLazyZ>(D, n0, n1, n2, d4, g, out, ne, nf);
+    out.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+    out.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+    out.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
     out.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
     out.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
 }
@@ -566,8 +594,27 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         // skip iff R (1 - 2^-20) - m_geo - mc > wbest; tested as R - m_geo > wthr with the
                         // warp-uniform wthr = (wbest + mc)(1 + 2^-18), which implies it (m_geo >= 0)
                         GPP_STAT(0, 1);
-                        eval_pair_fast<true, 2, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                        const f2 R = resid_sum(h);
+                        const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
+                        // stage 1: the bottom face only (three of the six residuals, nothing that involves X_t).  Their
+                        // sum is a lower bound of the residual sum, and the part of the margin that belongs to the
+                        // points on the plane (w ms <= m_geo) bounds its error: ~3 of 4 iterations end here.
+                        Bottom g;
+                        eval_bottom<true, true>(D, n0, n1, n2, d4, g);
+                        h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+                        h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+                        h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+                        const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
+                        {
+                            const f2 Slo = fma2(neg2(g.w), bc(D.ms), S3);
+                            if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) continue;
+                        }
+                        GPP_STAT(3, 1);
+                        // stage 2: X_t, the height and the two slanted edges, the full margin
+                        f2 ne, nf;
+                        eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+                        h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+                        h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+                        const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
                         const f2 Rlo = sub2(R, h.m);
                         trig0 = !(lo(Rlo) > wthr);
                         trig1 = !(hi(Rlo) > wthr);
@@ -582,7 +629,6 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         trig0 = trig0 && !(lo(rlo) > 0.7f);
                         trig1 = trig1 && !(hi(rlo) > 0.7f);
                         if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
-                        GPP_STAT(3, 1);
                         h.finish_zc();
                         const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
                         const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
