@@ -728,7 +728,23 @@ GPP_UNROLL(GPP_M6_UNROLL)
                         }
                     }
                 } else {
-                    eval_pair_fast<true, 0, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    // two stages like the VERIFIED all-six phase: the three bottom-face residuals first; their sum never
+                    // exceeds the full sum (floating-point addition of non-negative terms is monotone), so leaving
+                    // here decides exactly what the full test below would decide
+                    const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
+                    Bottom g;
+                    eval_bottom<true, false>(D, n0, n1, n2, d4, g);
+                    h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+                    h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+                    h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+                    {
+                        const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
+                        if (!__any_sync(0xffffffffu, !(lo(S3) > wbest) || !(hi(S3) > wbest))) continue;
+                    }
+                    f2 ne, nf;
+                    eval_top<0, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+                    h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+                    h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
                     const f2 R = resid_sum(h);
                     // only a pair that scores no worse than the warp's best so far can change the result
                     if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
