@@ -20,7 +20,11 @@ namespace gpp {
 #define GPP_WARPS 8
 #endif
 constexpr int kWarps = GPP_WARPS;
+#ifdef GPP_MB_OVERRIDE
+#define GPP_MB(x) GPP_MB_OVERRIDE            /* experiments: resident CTAs per SM given directly */
+#else
 #define GPP_MB(x) ((x) * 8 / GPP_WARPS)   /* resident CTAs per SM for x CTAs of 8 warps */
+#endif
 #ifndef GPP_TILE
 #define GPP_TILE 1024
 #endif
