@@ -547,7 +547,7 @@ int64_t gpp_launch_count(const gpp_handle *h) { return h ? h->launches : 0; }
 
 int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
                      int which, int32_t *votes, float *resid, int32_t *zneg, float *margin) {
-    if (!h || !box12 || !dims3 || !pinv12 || !votes || !resid || !zneg || h->n_planes <= 0 || which < 0 || which > 2)
+    if (!h || !box12 || !dims3 || !pinv12 || !votes || !resid || !zneg || h->n_planes <= 0 || which < 0 || which > 3)
         return set_error(GPP_EINVAL, "gpp_debug_scores: bad argument");
     DeviceGuard guard(h->device);
     const int n = h->n_planes;

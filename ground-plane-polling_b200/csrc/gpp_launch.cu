@@ -297,6 +297,34 @@ __global__ void scores_fast_kernel(PollArgs2<float> a, int32_t *votes, float *re
     }
 }
 
+// which == 3: stage 1 of the VERIFIED all-six phase -- resid = sum of the three bottom-face residuals (merged
+// reciprocals, as in the kernel), margin = the bound the stage-1 test relies on: w ms + mc + 2^-20 S3
+__global__ void scores_bottom_kernel(PollArgs2<float> a, int32_t *votes, float *resid, int32_t *zneg, float *margin) {
+    DetConst D;
+    {
+        Detection<ExactF32> det;
+        load_detection<ExactF32, ExactF32>(det, a.boxes, a.dims, a.orient[0], a.pinv);
+        for (int i = 0; i < 6; ++i) D.td[i] = det.td[i];
+        fast_constants(D, det);
+    }
+    const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.pairs);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p < a.n_planes; p += gridDim.x * blockDim.x) {
+        const ulonglong2 v0 = pairs[2 * p], v1 = pairs[2 * p + 1];
+        Bottom g;
+        eval_bottom<true, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), g);
+        const f2 r1 = sub2(PackFast::sqrt(g.na), bc(D.td[1])), r2 = sub2(PackFast::sqrt(g.nb), bc(D.td[2])),
+                 r3 = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+        const f2 S3 = add2(add2(abs2(r1), abs2(r2)), abs2(r3));
+        const f2 m1 = fma2(S3, bc(9.5367431640625e-07f), fma2(g.w, bc(D.ms), bc(D.mc)));
+        votes[2 * p] = 0; zneg[2 * p] = 0; resid[2 * p] = lo(S3);
+        if (margin) margin[2 * p] = lo(m1);
+        if (2 * p + 1 < a.n_planes) {
+            votes[2 * p + 1] = 0; zneg[2 * p + 1] = 0; resid[2 * p + 1] = hi(S3);
+            if (margin) margin[2 * p + 1] = hi(m1);
+        }
+    }
+}
+
 int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const int32_t *d_orient, int which,
                   int32_t *votes, float *resid, int32_t *zneg, float *margin, cudaStream_t s) {
     const int threads = 128, blocks = 64;
@@ -312,7 +340,8 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
         b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
         b.n_pairs_padded = h->n_pairs_padded;
         if (which == 1) scores_fast_kernel<false><<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
-        else scores_fast_kernel<true><<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
+        else if (which == 2) scores_fast_kernel<true><<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
+        else scores_bottom_kernel<<<blocks, threads, 0, s>>>(b, votes, resid, zneg, margin);
     }
     h->launches += 1;
     cudaError_t e = cudaGetLastError();

@@ -205,7 +205,7 @@ class PlanePoller(object):
     def debug_scores(self, box12, dims3, orientation, pinv12, which=0, with_margin=False):
         """Test hook: (votes, residual sum, z_dir_check < 0 [, margin]) of one detection against every
         resident plane, from the device functions of the search loop (which: 0 exact, 1 fast general, 2 fast
-        all-six path); margin = the VERIFIED mode's bound on |fast - exact| of the residual sum."""
+        all-six path, 3 stage 1 of the verified all-six path: bottom-face residual sum and its margin); margin = the VERIFIED mode's bound on |fast - exact| of the residual sum."""
         n = self.num_planes
         votes, zneg, resid = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32)
         margin = np.zeros(n, np.float32) if with_margin else None

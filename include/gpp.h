@@ -179,8 +179,10 @@ int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
 
 /* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same
  * device functions the search loops call -- `which` 0 = EXACT arithmetic, 1 = FAST (general path), 2 = FAST
- * (all-six-votes path, merged reciprocal).  votes / zneg: N int32, resid: N floats (host memory); margin: N
- * floats or NULL -- the VERIFIED mode's bound on |fast - exact| of the residual sum (0 for which = 0). */
+ * (all-six-votes path, merged reciprocal), 3 = stage 1 of the VERIFIED all-six path (resid = sum of the three
+ * bottom-face residuals, margin = the bound its early exit relies on; votes / zneg are zero).  votes / zneg: N
+ * int32, resid: N floats (host memory); margin: N floats or NULL -- the VERIFIED mode's bound on |fast - exact| of
+ * the residual sum (0 for which = 0). */
 int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
                      int which, int32_t *votes, float *resid, int32_t *zneg, float *margin);
 

@@ -74,6 +74,46 @@ def test_verified_equals_exact_on_a_config4_slice(gpp):
     _same(host, [t[:700].cpu().numpy() for t in ex])
 
 
+def _oracle_bottom3(boxes, dims, orient, P_inv, planes, b, d):
+    """EXACT-arithmetic sum of the three bottom-face residuals (|X_l-X_m|, |X_m-X_r|, |X_l-X_r| against their
+    targets) of one detection against every plane, float32 like the oracle."""
+    from oracle import fit_road_planes_ref as R
+    f = np.float32
+    bx, dm, pi, pl = R._feed(boxes, dims, P_inv, planes, f)
+    npl = R.normalise_planes(pl[0] if pl.ndim == 3 else pl, f)
+    rays = R.detection_rays(bx, pi, f)
+    td = R.detection_dims(dm, orient, f)
+    (Xl, Xm, Xr, Xt), votes, resid, zc = R.hypotheses(rays[b, d:d + 1], td[b, d:d + 1], npl, f)
+    with np.errstate(all='ignore'):
+        r1 = np.abs(R._dist(Xl, Xm) - td[b, d, 1])
+        r2 = np.abs(R._dist(Xm, Xr) - td[b, d, 2])
+        r3 = np.abs(R._dist(Xl, Xr) - td[b, d, 3])
+        return ((r1 + r2) + r3)[0].astype(f)
+
+
+def test_stage_one_margin_bounds_the_bottom_face_sum(poller):
+    """Stage 1 of the all-six phase stops on S3 - (w ms + mc + 2^-20 S3) > best, S3 = fast sum of the three
+    bottom-face residuals: that margin is at least 4x the observed |fast - exact| deviation of S3 wherever it could
+    matter, and S3 (exact) never exceeds the exact residual sum."""
+    planes = load_planes('22k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 16, planes, seed=212, kp_noise_px=3.0)
+    poller.set_planes(planes)
+    worst = 0.0
+    for b in range(3):
+        for d in range(16):
+            out = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=3, with_margin=True)
+            s3_fast, m1 = out[1], out[3]
+            s3_exact = _oracle_bottom3(boxes, dims, orient, P_inv, planes, b, d)
+            ev, er, ez = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_inv[b], which=0)
+            fin = np.isfinite(er) & np.isfinite(s3_exact)
+            assert (s3_exact[fin] <= er[fin]).all()                # a lower bound of the residual sum
+            rel = fin & (er < 6 * 0.7 + 1.0) & np.isfinite(s3_fast)
+            assert np.isfinite(m1[rel]).all() and (m1[rel] > 0).all()
+            ratio = np.abs(s3_fast[rel] - s3_exact[rel]) / m1[rel]
+            worst = max(worst, float(ratio.max()) if ratio.size else 0.0)
+    assert worst < 0.25, worst
+
+
 def test_margin_bounds_the_fast_vs_exact_deviation(poller):
     """Per hypothesis, wherever it could matter (exact: six votes or close to it, finite): the filter's
     margin is at least 4x the observed |fast - exact| deviation of the residual sum, and the loosened vote /
@@ -164,3 +204,7 @@ def test_verified_is_robust_to_ray_scale_and_odd_geometry(gpp, poller, ray_scale
             assert zok[~ez].all()
             fin = np.isfinite(er) & np.isfinite(fr)
             assert (np.abs(fr[fin] - er[fin]) <= fm[fin]).all()
+        out = poller.debug_scores(boxes[b, d], dims[b, d], orient[b, d], P_scaled[b], which=3, with_margin=True)
+        s3_exact = _oracle_bottom3(boxes, dims, orient, P_scaled, planes, b, d)
+        fin = np.isfinite(s3_exact) & np.isfinite(out[1])
+        assert (np.abs(out[1][fin] - s3_exact[fin]) <= out[3][fin]).all()         # stage-1 margin, odd geometry
