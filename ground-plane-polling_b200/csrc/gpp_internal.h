@@ -85,7 +85,7 @@ struct gpp_handle {
     int force_variant = 0, force_ctas_per_sm = 0;
     int occ[3] = {0, 0, 0};                      // resident CTAs per SM: exact dpw 1, exact dpw 2, fp64
     int occ2[3] = {0, 0, 0};                     // fast kernel: [register-budget variant]
-    int occ3[2] = {0, 0};                        // verified kernel: [register-budget variant]
+    int occ3[3] = {0, 0, 0};                        // verified kernel: [register-budget variant]
     int occ_split[4] = {0, 0, 0, 0};             // small-batch (one detection per CTA) kernels: exact, fast, verified, f64
     int force_split = 0;                         // tuning hook: > 0 force the small-batch kernels, < 0 forbid them
 };

@@ -10,7 +10,7 @@
 #define GPP_DEFAULT_VARIANT_FAST 1
 #endif
 #ifndef GPP_DEFAULT_VARIANT_VERIFIED
-#define GPP_DEFAULT_VARIANT_VERIFIED 1
+#define GPP_DEFAULT_VARIANT_VERIFIED 2
 #endif
 
 namespace gpp {
@@ -33,6 +33,12 @@ constexpr int kWarps = GPP_WARPS;
 #endif
 constexpr int kTile32 = GPP_TILE, kTile64 = 512;
 constexpr int kStages = GPP_STAGES;
+// the packed kernels run a deeper ring: with per-warp claiming (kFree) a fast warp can bank up to three tiles of
+// lead over the slowest warp of its CTA (4 x 16 KB tiles + queues = 69 KB per CTA, three CTAs per SM)
+#ifndef GPP_STAGES2
+#define GPP_STAGES2 4
+#endif
+constexpr int kStages2 = GPP_STAGES2;
 
 // pair-interleaved, padded copy of the normalised fp32 database: pair p = planes (2p, 2p+1) stored as
 // {a0,a1,b0,b1,c0,c1,d0,d1}; planes past N-1 are copies of plane N-1 (same score, higher index: they can
@@ -128,9 +134,9 @@ static long long grid_for(const gpp_handle *h, long long n_groups, int occ) {
     return grid < 1 ? 1 : grid;
 }
 
-constexpr size_t kSmem2 = size_t(32) * kStages * (kTile32 / 2) + 2 * kStages * sizeof(uint64_t) +
+constexpr size_t kSmem2 = size_t(32) * kStages2 * (kTile32 / 2) + 2 * kStages2 * sizeof(uint64_t) +
                           sizeof(int) * kWarps * kVerifyQueue + 2 * kWarps * sizeof(WarpPartial<float>) +
-                          2 * sizeof(unsigned int) + sizeof(float) * 20 * kWarps;
+                          2 * sizeof(unsigned int) + sizeof(float) * 20 * kWarps + 16;   // + need_until, active (kFree)
 constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * sizeof(uint64_t) +
                            2 * kWarps * sizeof(WarpPartial<double>);
 #define GPP_K_F64 poll_kernel<ExactF64, kWarps, 1, kTile64, kStages>
@@ -142,8 +148,8 @@ constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * s
 #define GPP_K_EXACT1 poll_kernel<ExactF32, kWarps, 1, kTile32, kStages>
 #define GPP_K_EXACT2 poll_kernel<ExactF32, kWarps, 2, kTile32, kStages>
 #define GPP_K_EXACT_SPLIT poll_kernel<ExactF32, kWarps, 1, kTile32, kStages, true>
-#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 0, true>
-#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 1, true>
+#define GPP_K_FAST_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(3), 0, true>
+#define GPP_K_VERIFIED_SPLIT poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(3), 1, true>
 constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
                           2 * kWarps * sizeof(WarpPartial<float>);
 
@@ -151,15 +157,16 @@ constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * siz
 typedef void (*Poll2Fn)(const PollArgs2<float>);
 static Poll2Fn fast_variant(int v) {
     switch (v) {
-        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(2)>;
-        case 1: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3)>;
-        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(4)>;
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(2)>;
+        case 1: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(3)>;
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(4)>;
     }
 }
 static Poll2Fn verified_variant(int v) {
     switch (v) {
-        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(2), 1>;
-        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages, GPP_MB(3), 1>;
+        case 0: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(2), 1>;
+        case 2: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(3), 1, false, true>;   // per-warp claiming (default)
+        default: return poll2_kernel<PackFast, kWarps, kTile32, kStages2, GPP_MB(3), 1>;
     }
 }
 
@@ -169,7 +176,7 @@ int configure_kernels(gpp_handle *h) {
     if ((rc = configure_kernel(GPP_K_EXACT2, kSmem1, &h->occ[1]))) return rc;
     for (int v = 0; v < 3; ++v)
         if ((rc = configure_kernel(fast_variant(v), kSmem2, &h->occ2[v]))) return rc;
-    for (int v = 0; v < 2; ++v)
+    for (int v = 0; v < 3; ++v)
         if ((rc = configure_kernel(verified_variant(v), kSmem2, &h->occ3[v]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64, kSmem64, &h->occ[2]))) return rc;
     if ((rc = configure_kernel(GPP_K_EXACT_SPLIT, kSmem1, &h->occ_split[0]))) return rc;
@@ -368,7 +375,7 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
         const long long n_groups = split ? a.n_det : (a.n_det + kWarps - 1) / kWarps;
         if (mode == GPP_MODE_VERIFIED) {
             int v = GPP_DEFAULT_VARIANT_VERIFIED;
-            if (h->force_variant >= 2 && h->force_variant <= 3) v = h->force_variant - 2;
+            if (h->force_variant >= 2 && h->force_variant <= 4) v = h->force_variant - 2;
             if (split) {
                 GPP_K_VERIFIED_SPLIT<<<(unsigned)grid_for(h, n_groups, h->occ_split[2]), kWarps * 32, kSmem2, s>>>(b);
             } else {

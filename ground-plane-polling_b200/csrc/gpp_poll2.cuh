@@ -423,8 +423,14 @@ __device__ __forceinline__ int strict_votes(const PairResult &h, bool upper) {
 // kVMode: 0 = plain FAST search, 1 = VERIFIED.  The verified filter has two warp-uniform phases: while the
 // warp's exact max-votes is below 6 it counts the votes that are possible within the margin (general phase);
 // once a plane with six exact votes is known it tests max_k |r_k| - m <= 0.7 (all-six-votes phase).
-template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, int kVMode = 0, bool kSplit = false>
+// kFree (VERIFIED, not kSplit): no detection groups and no CTA barrier.  Every warp claims its detections from the
+// device counter on its own and starts each one at whatever tile the CTA's ring currently delivers (the database
+// is scanned in rotated order, which the explicit index tie-breaks of the exact bookkeeping allow); the ring runs
+// as long as any warp needs tiles (`need_until`), warps that ran out of work keep releasing tiles until all are done.
+template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, int kVMode = 0, bool kSplit = false,
+          bool kFree = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
+    static_assert(!kFree || (kVMode != 0 && !kSplit), "kFree is implemented for the VERIFIED batch kernel");
     constexpr bool kVerified = kVMode != 0;
     constexpr int kTilePairs = kTile / 2;
     constexpr int kRowStep = kSplit ? kWarps : 1;
@@ -447,6 +453,12 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
     const long long n_groups = kSplit ? n_work : (n_work + kWarps - 1) / kWarps;
     unsigned int *claim = reinterpret_cast<unsigned int *>(partial + 2 * kWarps);       // [2]: groups k, k+1
     float *detx = reinterpret_cast<float *>(claim + 2) + (threadIdx.x >> 5) * 20;       // this warp's exact constants
+    // kFree: one past the last tile sequence number any warp has announced it needs / warps that still have work
+    static_assert((size_t(32) * kStages * kTilePairs + 2 * kStages * sizeof(uint64_t) + sizeof(int) * kWarps * kVerifyQueue +
+                   2 * kWarps * sizeof(WarpPartial<float>) + 2 * sizeof(unsigned int) + sizeof(float) * 20 * kWarps) % 8 == 0,
+                  "need_until must be 8-byte aligned");
+    unsigned long long *need_until = reinterpret_cast<unsigned long long *>(reinterpret_cast<float *>(claim + 2) + kWarps * 20);
+    int *active = reinterpret_cast<int *>(need_until + 1);
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -455,8 +467,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
             mbar_init(&empty_bar[s], kWarps);
         }
         mbar_fence_init();
-        claim[0] = atomicAdd(args.group_counter, 1u);
-        claim[1] = atomicAdd(args.group_counter, 1u);
+        if (kFree) {
+            *need_until = 0ull;
+            *active = kWarps;
+        } else {
+            claim[0] = atomicAdd(args.group_counter, 1u);
+            claim[1] = atomicAdd(args.group_counter, 1u);
+        }
     }
     __syncthreads();
 
@@ -481,19 +498,46 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         }
     };
 
-    long long it = 0;
-    for (long long k = 0;; ++k) {
-        const unsigned int g32 = claim[k & 1], g_next = claim[(k + 1) & 1];
-        if (g32 >= n_groups) break;                                  // CTA-uniform
-        __syncthreads();                                             // everyone has read claim[k & 1]
-        if (threadIdx.x == 0) {
-            claim[k & 1] = atomicAdd(args.group_counter, 1u);        // group k + 2
-            known_tiles = (k + 1 + (g_next < n_groups ? 1 : 0)) * n_tiles;
-            pump(it - 1 + kStages);
+    auto pump_free = [&](long long max_index) {                     // kFree: bounded by the announced need instead
+        const long long need = (long long)*reinterpret_cast<volatile unsigned long long *>(need_until);
+        while (issued < need && issued <= max_index) {
+            if (issued >= kStages)
+                mbar_wait(&empty_bar[issued % kStages], uint32_t(((issued / kStages) - 1) & 1));
+            issue(issued);
+            ++issued;
         }
-        const long long g = g32;
+    };
+
+    long long it = 0;
+    unsigned int next_claim = 0;
+    if (kFree) {
+        if (lane == 0) next_claim = atomicAdd(args.group_counter, 1u);
+        next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+    }
+    for (long long k = 0;; ++k) {
+        long long w_id;
+        if (kFree) {
+            const unsigned int cur = next_claim;
+            if ((long long)cur >= n_work) break;                         // warp-uniform: this warp retires
+            if (lane == 0) {
+                atomicMax(need_until, (unsigned long long)(it + n_tiles));   // announced before anything waits for it
+                next_claim = atomicAdd(args.group_counter, 1u);              // claimed one detection ahead
+            }
+            next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+            w_id = cur;
+        } else {
+            const unsigned int g32 = claim[k & 1], g_next = claim[(k + 1) & 1];
+            if (g32 >= n_groups) break;                                  // CTA-uniform
+            __syncthreads();                                             // everyone has read claim[k & 1]
+            if (threadIdx.x == 0) {
+                claim[k & 1] = atomicAdd(args.group_counter, 1u);        // group k + 2
+                known_tiles = (k + 1 + (g_next < n_groups ? 1 : 0)) * n_tiles;
+                pump(it - 1 + kStages);
+            }
+            const long long g = g32;
+            w_id = kSplit ? g : g * kWarps + warp;
+        }
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
-        const long long w_id = kSplit ? g : g * kWarps + warp;
         long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
         if (args.det_list) mm = args.det_list[mm];
         const long long m = w_id < n_work ? mm : args.n_det;       // >= n_det: nothing is written
@@ -539,8 +583,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const Po
         unsigned int st_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 1};
 #endif
 
-        for (int t = 0; t < n_tiles; ++t, ++it) {
+        for (int tt = 0; tt < n_tiles; ++tt, ++it) {
+            const int t = kFree ? int(it % n_tiles) : tt;            // kFree: wherever the ring is
             const int s = int(it % kStages);
+            if (kFree && threadIdx.x == 0) pump_free(it - 1 + kStages);   // tile `it` itself may not be issued yet
             mbar_wait(&full_bar[s], uint32_t((it / kStages) & 1));
             const ulonglong2 *tile = tiles + size_t(s) * kTilePairs * 2;
             const int rows = min(kTilePairs, NP - t * kTilePairs) >> 5;
@@ -759,7 +805,7 @@ GPP_UNROLL(GPP_M6_UNROLL)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (threadIdx.x == 0) pump(it - 1 + kStages);      // skewed by one tile: rarely waits for the slowest warp
+            if (!kFree && threadIdx.x == 0) pump(it - 1 + kStages);   // skewed by one tile: rarely waits for the slowest warp
             __syncwarp();
         }
 
@@ -857,6 +903,29 @@ GPP_UNROLL(GPP_M6_UNROLL)
             kpl[0] = pl.x; kpl[1] = pl.y; kpl[2] = pl.z; kpl[3] = pl.w;
             args.residuals[m] = __fdiv_rn(rr, 6.0f);
             if (args.best) args.best[m] = idx;
+        }
+    }
+    if (kFree) {
+        // ---- out of work: keep releasing the tiles the other warps still stream, leave when nobody needs any
+        __syncwarp();
+        if (lane == 0) atomicSub(active, 1);          // every announcement of this warp precedes this
+        for (;;) {
+            const long long need = (long long)*reinterpret_cast<volatile unsigned long long *>(need_until);
+            if (it < need) {
+                const int s = int(it % kStages);
+                if (threadIdx.x == 0) pump_free(it - 1 + kStages);
+                mbar_wait(&full_bar[s], uint32_t((it / kStages) & 1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                ++it;
+                continue;
+            }
+            if (*reinterpret_cast<volatile int *>(active) == 0) {
+                __threadfence_block();
+                if (it >= (long long)*reinterpret_cast<volatile unsigned long long *>(need_until)) break;
+            } else {
+                __nanosleep(500);
+            }
         }
     }
 }

@@ -208,3 +208,24 @@ def test_verified_is_robust_to_ray_scale_and_odd_geometry(gpp, poller, ray_scale
         s3_exact = _oracle_bottom3(boxes, dims, orient, P_scaled, planes, b, d)
         fin = np.isfinite(s3_exact) & np.isfinite(out[1])
         assert (np.abs(out[1][fin] - s3_exact[fin]) <= out[3][fin]).all()         # stage-1 margin, odd geometry
+
+
+@pytest.mark.parametrize('variant', [2, 3, 4])
+def test_every_verified_batch_kernel_variant_equals_the_oracle(gpp, poller, variant):
+    """The verified batch kernels -- group-synchronous with 2 / 3 CTAs per SM (variants 2, 3) and the default with
+    per-warp claiming and a rotated scan (variant 4) -- forced on inputs with padding rows, detections without six
+    votes, duplicates in the database and fewer detections than warps."""
+    planes = load_planes('10k')[:7001]                     # ragged last tile, duplicate rows of the 10k database
+    boxes, dims, orient, P_inv = synthetic.synth_detections(9, 60, planes, seed=505, n_valid=41, kp_noise_px=4.0)
+    dims = dims.copy()
+    dims[2, :12, 0] *= 1.6
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    poller.debug_set_config(200 + variant, 0)
+    try:
+        _same(gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True), want)
+        few = gpp.fit_road_planes(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes, mode='verified',
+                                  return_index=True)
+        _same(few, c_oracle.fit_road_planes_c(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes,
+                                              return_index=True))
+    finally:
+        poller.debug_set_config(0, 0)
