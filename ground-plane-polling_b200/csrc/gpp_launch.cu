@@ -1,5 +1,5 @@
-// Kernel instantiations and launch configuration of the polling kernels (gpp_poll2.cuh: packed-pair fp32
-// modes; gpp_poll.cuh: scalar kernel, used for the FP64 verify mode).
+// Kernel instantiations and launch configuration of the polling kernels (gpp_poll2.cuh: packed-pair kernels of
+// the FAST and VERIFIED modes; gpp_poll.cuh: scalar kernel of the EXACT and FP64 modes).
 #ifdef GPP_STATS
 #include <cstdio>
 #endif

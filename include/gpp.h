@@ -171,10 +171,11 @@ int64_t gpp_launch_count(const gpp_handle *h);
  * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
 
-/* Tuning hook (benchmarks only): `variant` 2 / 3 / 4 selects the fp32 kernel compiled for that many resident
- * CTAs per SM (register budget 128 / 80 / 64; 0 = built-in default); +100 forces, +200 forbids the small-batch
- * kernels (one detection per CTA, planes split over the warps; default: automatic by batch size);
- * `ctas_per_sm` sizes the persistent grid (0 = occupancy maximum). */
+/* Tuning / test hook: `variant` selects the batch kernel of the packed fp32 modes (0 = built-in default).
+ * FAST: 2 / 3 / 4 = the kernel compiled for that many resident CTAs per SM (register budget 128 / 80 / 64).
+ * VERIFIED: 2 / 3 = group-synchronous kernel with 2 / 3 CTAs per SM, 4 = per-warp claiming with a rotated scan
+ * (the default).  +100 forces, +200 forbids the small-batch kernels (one detection per CTA, planes split over the
+ * warps; default: automatic by batch size); `ctas_per_sm` sizes the persistent grid (0 = occupancy maximum). */
 int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
 
 /* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same
