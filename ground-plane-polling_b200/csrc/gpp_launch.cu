@@ -406,7 +406,11 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
     } else {
         // two detections per warp once every SM has several groups to chew on
         const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
+#ifdef GPP_EXACT_NO_DPW2
+        const bool two = false;
+#else
         const bool two = a.n_det >= 4 * resident;
+#endif
         if (two) {
             const long long n_groups = (a.n_det + 2 * kWarps - 1) / (2 * kWarps);
             GPP_K_EXACT2<<<(unsigned)grid_for(h, n_groups, h->occ[1]), kWarps * 32, kSmem1, s>>>(a);

@@ -135,6 +135,16 @@ __device__ __forceinline__ double warp_min_first(double v, int &idx) {
     return v;
 }
 
+// warp-wide minimum of a non-negative, non-NaN value
+__device__ __forceinline__ float warp_min_value(float v) {
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ double warp_min_value(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // ------------------------------------------------------------------ the kernel
 // partial result of one warp when the warps of a CTA split the planes of ONE detection (small batches)
 template <class T>
@@ -197,6 +207,13 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
     LaneState<T> st[kDpw];
     long long det_id[kDpw];
     const T highest = P::highest();
+    // Once a plane with six votes is known (warp-uniform m6), a plane matters only if its residual sum does not
+    // exceed the warp's best six-vote residual wbest.  The sum of the three bottom-face residuals never exceeds
+    // the full sum (rounded addition of non-negative terms is monotone; a NaN / inf sum never wins), so
+    // (r1 + r2) + r3 > wbest for all 32 lanes ends the hypothesis after its first half: X_t, one division and
+    // three square roots are skipped for about three of four rows, and nothing that is kept changes by a bit.
+    bool m6[kDpw];
+    T wbest[kDpw];
 
     long long it = 0;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -210,6 +227,8 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
             load_detection<P, typename ExactOf<P>::type>(det[q], args.boxes + 12 * mm, args.dims + 3 * mm, __ldg(args.orient + mm),
                                  args.pinv + 12 * (mm / args.dets_per_image));
             st[q].reset(highest);
+            m6[q] = false;
+            wbest[q] = highest;
         }
         // ---- stream the whole database through the ring
         for (int t = 0; t < n_tiles; ++t, ++it) {
@@ -229,8 +248,26 @@ __global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typena
                 for (int q = 0; q < kDpw; ++q) {
                     T X[4][3];
                     int V; T R; bool zneg;
-                    hypothesis<P>(det[q], pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
-                    st[q].update(V, R, zneg, base + jj, highest);
+                    if (m6[q]) {
+                        T rb[3];
+                        hypothesis_bottom<P>(det[q], pl.x, pl.y, pl.z, pl.w, X, rb, zneg);
+                        const T S3 = P::add(P::add(rb[0], rb[1]), rb[2]);
+                        if (!__any_sync(0xffffffffu, !(S3 > wbest[q]))) continue;
+                        hypothesis_top<P>(det[q], pl.x, pl.y, pl.z, X, rb, V, R);
+                        st[q].update(V, R, zneg, base + jj, highest);
+                        wbest[q] = warp_min_value(st[q].M == 6 ? st[q].bestR : highest);
+                    } else {
+                        hypothesis<P>(det[q], pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+                        st[q].update(V, R, zneg, base + jj, highest);
+                    }
+                }
+                if (((r / kRowStep) & 3) == 3) {
+#pragma unroll
+                    for (int q = 0; q < kDpw; ++q)
+                        if (!m6[q] && __reduce_max_sync(0xffffffffu, st[q].M) == 6) {
+                            m6[q] = true;
+                            wbest[q] = warp_min_value(st[q].M == 6 ? st[q].bestR : highest);
+                        }
                 }
             }
             if ((cnt & 31) != 0 && (!kSplit || r == full_rows)) {   // ragged last row of the last tile
