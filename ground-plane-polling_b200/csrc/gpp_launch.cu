@@ -404,12 +404,12 @@ int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaSt
     } else if (use_split(h, a.n_det, 15)) {
         GPP_K_EXACT_SPLIT<<<(unsigned)grid_for(h, a.n_det, h->occ_split[0]), kWarps * 32, kSmem1, s>>>(a);
     } else {
-        // two detections per warp once every SM has several groups to chew on
         const long long resident = (long long)h->sm_count * h->occ[0] * kWarps;
-#ifdef GPP_EXACT_NO_DPW2
-        const bool two = false;
-#else
+#ifdef GPP_EXACT_DPW2   /* experiment: two detections per warp for large batches (slower since r01n) */
         const bool two = a.n_det >= 4 * resident;
+#else
+        const bool two = false;
+        (void)resident;
 #endif
         if (two) {
             const long long n_groups = (a.n_det + 2 * kWarps - 1) / (2 * kWarps);

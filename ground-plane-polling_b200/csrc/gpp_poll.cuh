@@ -157,7 +157,10 @@ struct WarpPartial {
 // kSplit: small-batch variant -- the CTA works on one detection, warp w takes the rows r = w (mod kWarps) of
 // every tile and the partial arg-mins are merged through shared memory (kDpw must be 1).
 template <class P, int kWarps, int kDpw, int kTile, int kStages, bool kSplit = false>
-__global__ void __launch_bounds__(kWarps * 32) poll_kernel(const PollArgs<typename P::T> args) {
+// the one-detection-per-warp fp32 kernel is capped at 64 registers: four CTAs per SM (measured best once the second
+// half of most hypotheses is skipped; the two-detections-per-warp variant needs 107 registers and is slower now)
+#define GPP_EXACT_BOUNDS __launch_bounds__(kWarps * 32, (sizeof(typename P::T) == 4 && kDpw == 1) ? 4 : 1)
+__global__ void GPP_EXACT_BOUNDS poll_kernel(const PollArgs<typename P::T> args) {
     typedef typename P::T T;
     typedef typename P::T4 T4;
     static_assert(!kSplit || kDpw == 1, "the split variant handles one detection per CTA");
