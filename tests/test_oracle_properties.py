@@ -87,3 +87,35 @@ def test_second_best_gap_helper():
     best, v1, v2, getter = second_best_gap(boxes, dims, orient, P_inv, planes)
     assert (v2 >= v1).all()
     assert getter(0, 0, int(best[0, 0])) == v1[0, 0]
+
+
+def test_partial_residual_sum_never_exceeds_the_full_sum():
+    """The kernels stop a hypothesis early when (r1 + r2) + r3 already exceeds the best residual sum.  That is exact
+    because rounded addition of non-negative terms is monotone: the reference's
+    ((((r0 + r1) + r2) + r3) + r4) + r5 is never below (r1 + r2) + r3, in float32 and float64, for any magnitudes."""
+    rng = np.random.default_rng(11)
+    for dt in (np.float32, np.float64):
+        n = 400000
+        mag = rng.choice([1e-30, 1e-7, 1e-3, 1.0, 37.5, 1e4, 1e20], size=(n, 6))
+        r = (rng.random((n, 6)) * mag).astype(dt)
+        r[rng.random((n, 6)) < 0.05] = 0
+        with np.errstate(over='ignore'):
+            full = ((((r[:, 0] + r[:, 1]) + r[:, 2]) + r[:, 3]) + r[:, 4]) + r[:, 5]
+            part = (r[:, 1] + r[:, 2]) + r[:, 3]
+        assert full.dtype == dt and (part <= full).all()
+        # the oracle's own residual sums obey it too (bottom-face residuals of real hypotheses)
+    from gpp_b200.utils import synthetic
+    from conftest import load_planes
+    from oracle import fit_road_planes_ref as R
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(1, 8, planes, seed=3)
+    f = np.float32
+    bx, dm, pi, pl = R._feed(boxes, dims, P_inv, planes[None], f)
+    npl = R.normalise_planes(pl[0], f)
+    rays = R.detection_rays(bx, pi, f).reshape(-1, 4, 3)
+    td = R.detection_dims(dm, orient, f).reshape(-1, 6)
+    (Xl, Xm, Xr, Xt), votes, resid, zc = R.hypotheses(rays, td, npl, f)
+    with np.errstate(all='ignore'):
+        s3 = (np.abs(R._dist(Xl, Xm) - td[:, 1:2]) + np.abs(R._dist(Xm, Xr) - td[:, 2:3])) + np.abs(R._dist(Xl, Xr) - td[:, 3:4])
+    ok = np.isfinite(resid)
+    assert (s3[ok] <= resid[ok]).all()
