@@ -18,7 +18,7 @@ c_int64_p = ctypes.POINTER(ctypes.c_int64)
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
 
-# name -> (restype, argtypes); mirrors include/gpp.h one to one (tests/test_capi.py checks the list)
+# name -> (restype, argtypes); mirrors include/gpp.h and include/gpp_debug.h one to one (tests/test_capi.py checks it)
 SIGNATURES = {
     'gpp_version': (c_int, []),
     'gpp_device_count': (c_int, []),
@@ -55,6 +55,9 @@ SIGNATURES = {
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),
     'gpp_debug_set_config': (c_int, [c_void_p, c_int, c_int]),
+    'gpp_debug_set_schedule': (c_int, [c_void_p, c_int, c_int]),
+    'gpp_audit_set': (c_int, [c_void_p, c_int]),
+    'gpp_audit_counts': (c_int, [c_void_p, c_int64_p, c_int64_p]),
     'gpp_debug_scores': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
 }

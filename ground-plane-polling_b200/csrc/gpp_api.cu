@@ -3,12 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
-#include "../../include/gpp.h"
+#include "../../include/gpp_debug.h"
 #include "gpp_internal.h"
 
 namespace {
@@ -146,6 +147,7 @@ int gpp_create(int device, gpp_handle **out) {
         gpp_destroy(h);
         return rc;
     }
+    if (const char *env = getenv("GPP_AUDIT")) h->audit_every = atoi(env) > 0 ? atoi(env) : 0;
     *out = h;
     return GPP_OK;
 }
@@ -161,6 +163,8 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->filter_keys);
     cudaFree(h->filter_orient);
     cudaFree(h->filter_counts);
+    gpp::release_poll3(h);
+    gpp::release_audit(h);
     for (auto &w : h->work) {
         cudaFree(w.list);
         cudaFree(w.ulist);
@@ -585,6 +589,32 @@ int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int 
     cudaFree(d_det); cudaFree(d_res); cudaFree(d_int);
     if (rc != GPP_OK) return rc;
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "gpp_debug_scores: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+int gpp_debug_set_schedule(gpp_handle *h, int n_seg, int resident_rows) {
+    if (!h || n_seg < 0 || n_seg > 32) return set_error(GPP_EINVAL, "gpp_debug_set_schedule: bad argument");
+    h->force_seg = n_seg;
+    h->force_resident = resident_rows < 0 ? -1 : resident_rows;
+    return GPP_OK;
+}
+
+int gpp_audit_set(gpp_handle *h, int every) {
+    if (!h || every < 0) return set_error(GPP_EINVAL, "gpp_audit_set: bad argument");
+    h->audit_every = every;
+    return GPP_OK;
+}
+
+int gpp_audit_counts(gpp_handle *h, int64_t *checked, int64_t *mismatches) {
+    if (!h) return set_error(GPP_EINVAL, "gpp_audit_counts: handle is NULL");
+    DeviceGuard guard(h->device);
+    unsigned long long c[2] = {0, 0};
+    if (h->audit_counts) {
+        GPP_CUDA(cudaDeviceSynchronize());
+        GPP_CUDA(cudaMemcpy(c, h->audit_counts, sizeof(c), cudaMemcpyDeviceToHost));
+    }
+    if (checked) *checked = (int64_t)c[0];
+    if (mismatches) *mismatches = (int64_t)c[1];
     return GPP_OK;
 }
 

@@ -7,7 +7,7 @@
 #include <utility>
 #include <vector>
 
-#include "gpp_poll2.cuh"
+#include "gpp_poll3.cuh"
 
 namespace gpp {
 
@@ -61,6 +61,31 @@ struct gpp_handle {
     static constexpr int kWorkSlots = 4;
     WorkSlot work[kWorkSlots];
     unsigned next_work = 0;
+    // resident-database kernel (gpp_poll3.cuh): self-resetting counters and the scratch of segmented detections, one
+    // set per slot so that launches in flight on different streams never share one
+    struct Slot3 {
+        unsigned long long *claim = nullptr;     // [2]
+        gpp::SegPartial *partials = nullptr;     // [seg_items_cap]
+        unsigned int *seg_arrived = nullptr;     // [seg_det_cap]
+        unsigned long long *seg_best = nullptr;  // [seg_det_cap]
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    static constexpr int kSlots3 = 4;
+    Slot3 slot3[kSlots3];
+    unsigned next_slot3 = 0;
+    long long seg_det_cap = 0, seg_items_cap = 0;
+    int resident_cap_rows = 0;               // rows of the pair database that fit into one SM's shared memory
+    int force_seg = 0, force_resident = -1;  // tuning / test hook (gpp_debug_set_schedule): 0 / -1 = automatic
+    // runtime audit of the VERIFIED mode (gpp_audit_set): every n-th detection re-polled in the EXACT arithmetic
+    int audit_every = 0;
+    long long audit_cap = 0;
+    float *audit_out = nullptr;              // key-points, key-planes, residuals of the audit pass (17 floats per row)
+    long long *audit_best = nullptr, *audit_best_main = nullptr, *audit_list = nullptr;
+    unsigned int *audit_count = nullptr;
+    unsigned long long *audit_counts = nullptr;   // [0] rows checked, [1] rows that differ
+    cudaEvent_t audit_done = nullptr;
+    bool audit_used = false;
     unsigned long long *d_pairs = nullptr;   // pair-interleaved fp32 copy, padded to 64 planes (gpp_poll2.cuh)
     int n_pairs_padded = 0;
     int n_planes = 0, cap_planes = 0;
@@ -93,6 +118,8 @@ struct gpp_handle {
 namespace gpp {
 
 int configure_kernels(gpp_handle *h);
+void release_poll3(gpp_handle *h);
+void release_audit(gpp_handle *h);
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s);
 int build_pairs(gpp_handle *h, cudaStream_t s);
 int launch_scores(gpp_handle *h, const float *d_det, const int32_t *d_orient, int which, int32_t *votes,

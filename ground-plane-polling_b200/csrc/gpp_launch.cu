@@ -3,7 +3,7 @@
 #ifdef GPP_STATS
 #include <cstdio>
 #endif
-#include "../../include/gpp.h"
+#include "../../include/gpp_debug.h"
 #include "gpp_internal.h"
 
 #ifndef GPP_DEFAULT_VARIANT_FAST
@@ -153,6 +153,105 @@ constexpr size_t kSmem64 = sizeof(double4) * kStages * kTile64 + 2 * kStages * s
 constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * sizeof(uint64_t) +
                           2 * kWarps * sizeof(WarpPartial<float>);
 
+// Resident-database kernel (gpp_poll3.cuh): one persistent CTA of kWarps3 warps per SM
+#ifndef GPP_WARPS3
+#define GPP_WARPS3 24
+#endif
+constexpr int kWarps3 = GPP_WARPS3;
+typedef void (*Poll3Fn)(const PollArgs3);
+static Poll3Fn poll3_variant(bool verified, bool seg) {
+    if (verified) return seg ? poll3_kernel<kWarps3, 1, true> : poll3_kernel<kWarps3, 1, false>;
+    return seg ? poll3_kernel<kWarps3, 0, true> : poll3_kernel<kWarps3, 0, false>;
+}
+
+static int configure_poll3(gpp_handle *h) {
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "shared memory query: %s", cudaGetErrorString(e));
+    cudaFuncAttributes fa;
+    size_t fixed = 0;
+    for (int v = 0; v < 4; ++v) {
+        e = cudaFuncGetAttributes(&fa, poll3_variant(v & 1, v & 2));
+        if (e != cudaSuccess) return set_error(GPP_ECUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+        if (fa.sharedSizeBytes > fixed) fixed = fa.sharedSizeBytes;
+    }
+    const long long room = (long long)optin - (long long)fixed - (long long)smem3_bytes(kWarps3, 0);
+    if (room < 0) return set_error(GPP_ECUDA, "resident polling kernel does not fit on an SM");
+    h->resident_cap_rows = (int)(room / 1024);
+    const int max_dyn = (int)smem3_bytes(kWarps3, h->resident_cap_rows);
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v)
+        e = cudaFuncSetAttribute(poll3_variant(v & 1, v & 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    // scratch of segmented detections: segments are only used below 3 detections per resident warp
+    const long long slots = (long long)h->sm_count * kWarps3;
+    h->seg_det_cap = 3 * slots;
+    h->seg_items_cap = 6 * slots + 64;
+    for (int i = 0; i < gpp_handle::kSlots3 && e == cudaSuccess; ++i) {
+        gpp_handle::Slot3 &w = h->slot3[i];
+        e = cudaMalloc(&w.claim, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(w.claim, 0, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&w.partials, sizeof(SegPartial) * (size_t)h->seg_items_cap);
+        if (e == cudaSuccess) e = cudaMalloc(&w.seg_arrived, sizeof(unsigned int) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMemset(w.seg_arrived, 0, sizeof(unsigned int) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMalloc(&w.seg_best, sizeof(unsigned long long) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMemset(w.seg_best, 0, sizeof(unsigned long long) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll3 scratch allocation: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+void release_poll3(gpp_handle *h) {
+    for (auto &w : h->slot3) {
+        cudaFree(w.claim); cudaFree(w.partials); cudaFree(w.seg_arrived); cudaFree(w.seg_best);
+        if (w.done) cudaEventDestroy(w.done);
+        w = gpp_handle::Slot3();
+    }
+}
+
+// Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below three detections per resident warp every
+// detection is cut into plane segments so that the work items still fill the machine about three times over (the
+// last wave is then short whatever the batch size).  Residency: staging up to 216 KB per SM pays as soon as every
+// warp polls a few items; a call with fewer items than that streams every row from L2 and starts at once.
+static int launch_poll3(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
+    gpp_handle::Slot3 &w = h->slot3[h->next_slot3++ % gpp_handle::kSlots3];
+    cudaError_t e = cudaSuccess;
+    if (w.used) e = cudaStreamWaitEvent(s, w.done, 0);          // previous user of this slot (another stream)
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll3 slot: %s", cudaGetErrorString(e));
+    PollArgs3 b;
+    b.boxes = a.boxes; b.dims = a.dims; b.pinv = a.pinv; b.orient = a.orient;
+    b.pairs = h->d_pairs; b.planes = h->d_planes32; b.n_planes = h->n_planes;
+    b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = a.dets_per_image; b.n_det = a.n_det;
+    b.keypoints = a.keypoints; b.keyplanes = a.keyplanes; b.residuals = a.residuals; b.best = a.best;
+    b.claim = w.claim; b.partials = w.partials; b.seg_arrived = w.seg_arrived; b.seg_best = w.seg_best;
+    const int NR = h->n_pairs_padded / 32;
+    const long long slots = (long long)h->sm_count * kWarps3;
+    int n_seg = 1;
+    if (h->force_seg > 0) n_seg = h->force_seg;
+    else if (a.n_det < 3 * slots) n_seg = (int)((3 * slots + a.n_det - 1) / a.n_det);
+    if (n_seg > 32) n_seg = 32;
+    if (n_seg > NR) n_seg = NR;
+    if (a.n_det > h->seg_det_cap || a.n_det * n_seg > h->seg_items_cap) n_seg = 1;
+    b.rows_per_seg = (NR + n_seg - 1) / n_seg;
+    b.n_seg = (NR + b.rows_per_seg - 1) / b.rows_per_seg;
+    const long long n_items = a.n_det * b.n_seg;
+    int res = n_items >= 2 * slots ? h->resident_cap_rows : 0;
+    if (h->force_resident >= 0) res = h->force_resident;
+    if (res > h->resident_cap_rows) res = h->resident_cap_rows;
+    if (res > NR) res = NR;
+    b.resident_rows = res;
+    long long grid = h->sm_count;
+    if (grid > n_items) grid = n_items;
+    const size_t smem = smem3_bytes(kWarps3, res);
+    poll3_variant(mode == GPP_MODE_VERIFIED, b.n_seg > 1)<<<(unsigned)grid, kWarps3 * 32, smem, s>>>(b);
+    h->launches += 1;
+    w.used = true;
+    e = cudaEventRecord(w.done, s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "poll3 kernel launch: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
 // FAST kernel variants: v = 0..2 <-> __launch_bounds__(256, 2 / 3 / 4) i.e. <= 128 / 80 / 64 registers
 typedef void (*Poll2Fn)(const PollArgs2<float>);
 static Poll2Fn fast_variant(int v) {
@@ -183,6 +282,7 @@ int configure_kernels(gpp_handle *h) {
     if ((rc = configure_kernel(GPP_K_FAST_SPLIT, kSmem2, &h->occ_split[1]))) return rc;
     if ((rc = configure_kernel(GPP_K_VERIFIED_SPLIT, kSmem2, &h->occ_split[2]))) return rc;
     if ((rc = configure_kernel(GPP_K_F64_SPLIT, kSmem64, &h->occ_split[3]))) return rc;
+    if ((rc = configure_poll3(h))) return rc;
     return GPP_OK;
 }
 
@@ -356,7 +456,105 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
     return GPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Runtime audit of the VERIFIED mode (gpp_audit_set / GPP_AUDIT=n): every n-th detection of a call is polled again
+// by the EXACT kernel and compared with what the VERIFIED kernel wrote; the counters live on the device.
+// ---------------------------------------------------------------------------------------------------
+__global__ void audit_list_kernel(long long n_det, int every, long long n_sample, long long *list, unsigned int *count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = (unsigned int)n_sample;
+    if (i < n_sample) list[i] = i * every;
+}
+__global__ void audit_compare_kernel(const long long *list, long long n_sample, const long long *best_main,
+                                     const long long *best_exact, const float *res_main, const float *res_exact,
+                                     unsigned long long *counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool differs = false;
+    if (i < n_sample) {
+        const long long m = list[i];
+        differs = best_main[m] != best_exact[m] || __float_as_uint(res_main[m]) != __float_as_uint(res_exact[m]);
+    }
+    const unsigned bad = __popc(__ballot_sync(0xffffffffu, differs));
+    const unsigned seen = __popc(__ballot_sync(0xffffffffu, i < n_sample));
+    if ((threadIdx.x & 31) == 0) {
+        if (seen) atomicAdd(counts, (unsigned long long)seen);
+        if (bad) atomicAdd(counts + 1, (unsigned long long)bad);
+    }
+}
+
+void release_audit(gpp_handle *h) {
+    cudaFree(h->audit_out); cudaFree(h->audit_best); cudaFree(h->audit_best_main); cudaFree(h->audit_list);
+    cudaFree(h->audit_count); cudaFree(h->audit_counts);
+    if (h->audit_done) cudaEventDestroy(h->audit_done);
+    h->audit_out = nullptr; h->audit_best = h->audit_best_main = h->audit_list = nullptr;
+    h->audit_count = nullptr; h->audit_counts = nullptr; h->audit_done = nullptr; h->audit_cap = 0;
+}
+
+static int audit_reserve(gpp_handle *h, long long n_det, cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
+    if (!h->audit_counts) {
+        e = cudaMalloc(&h->audit_counts, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(h->audit_counts, 0, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&h->audit_count, sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->audit_done, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess && n_det > h->audit_cap) {
+        e = cudaDeviceSynchronize();
+        cudaFree(h->audit_out); cudaFree(h->audit_best); cudaFree(h->audit_best_main); cudaFree(h->audit_list);
+        h->audit_out = nullptr; h->audit_best = h->audit_best_main = h->audit_list = nullptr; h->audit_cap = 0;
+        if (e == cudaSuccess) e = cudaMalloc(&h->audit_out, sizeof(float) * 17 * (size_t)n_det);
+        if (e == cudaSuccess) e = cudaMalloc(&h->audit_best, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) e = cudaMalloc(&h->audit_best_main, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) e = cudaMalloc(&h->audit_list, sizeof(long long) * (size_t)n_det);
+        if (e == cudaSuccess) h->audit_cap = n_det;
+    }
+    // one set of audit buffers per handle: the previous audited call (possibly on another stream) must be through
+    if (e == cudaSuccess && h->audit_used) e = cudaStreamWaitEvent(s, h->audit_done, 0);
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "audit buffers: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+static int audit_pass(gpp_handle *h, const PollArgs<float> &a, cudaStream_t s) {
+    const int every = h->audit_every;
+    const long long n_sample = (a.n_det + every - 1) / every;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n_sample + threads - 1) / threads);
+    audit_list_kernel<<<blocks, threads, 0, s>>>(a.n_det, every, n_sample, h->audit_list, h->audit_count);
+    PollArgs<float> x = a;
+    x.keypoints = h->audit_out;
+    x.keyplanes = h->audit_out + 12 * a.n_det;
+    x.residuals = h->audit_out + 16 * a.n_det;
+    x.best = h->audit_best;
+    x.det_list = h->audit_list;
+    x.det_count = h->audit_count;
+    const long long n_groups = (n_sample + kWarps - 1) / kWarps;
+    GPP_K_EXACT1<<<(unsigned)grid_for(h, n_groups, h->occ[0]), kWarps * 32, kSmem1, s>>>(x);
+    audit_compare_kernel<<<blocks, threads, 0, s>>>(h->audit_list, n_sample, a.best, h->audit_best, a.residuals,
+                                                   x.residuals, h->audit_counts);
+    h->launches += 3;
+    h->audit_used = true;
+    cudaError_t e = cudaEventRecord(h->audit_done, s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(GPP_ECUDA, "audit pass: %s", cudaGetErrorString(e));
+    return GPP_OK;
+}
+
+static int launch_poll_f32_main(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaStream_t s);
+
 int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaStream_t s) {
+    if (mode != GPP_MODE_VERIFIED || h->audit_every <= 0) return launch_poll_f32_main(h, a_in, mode, s);
+    int rc = audit_reserve(h, a_in.n_det, s);
+    if (rc) return rc;
+    PollArgs<float> a = a_in;
+    if (!a.best) a.best = h->audit_best_main;
+    if ((rc = launch_poll_f32_main(h, a, mode, s))) return rc;
+    return audit_pass(h, a, s);
+}
+
+static int launch_poll_f32_main(gpp_handle *h, const PollArgs<float> &a_in, int mode, cudaStream_t s) {
+    // the packed modes run the resident-database kernel unless a test / tuning hook asks for a ring kernel
+    if ((mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) && h->force_variant == 0 && h->force_split == 0)
+        return launch_poll3(h, a_in, mode, s);
     gpp_handle::WorkSlot *w = nullptr;
     int rc = begin_unique(h, a_in, s, &w);
     if (rc) return rc;

@@ -2,7 +2,7 @@
 // rate, which MEASURED_PEAKS.json does not carry, so bench.py measures it in the same run.
 // Every kernel keeps 16 independent dependency chains per thread in registers, runs with all SMs full
 // (8 warps x 4 CTAs per SM) and reports both wall-clock rate and operations per SM clock.
-#include "../../include/gpp.h"
+#include "../../include/gpp_debug.h"
 #include "gpp_internal.h"
 
 namespace gpp {

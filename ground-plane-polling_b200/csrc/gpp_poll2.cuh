@@ -200,12 +200,17 @@ struct Bottom {
     f2 na, nb, nc;     // |X_l - X_m|^2, |X_r - X_m|^2, |X_l - X_r|^2
 };
 
-template <bool kMergedRcp, bool kMargin>
-__device__ __forceinline__ void eval_bottom(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, Bottom &g) {
+// eval_bottom comes in two steps so that a caller can let go of the plane registers in between (the resident kernel
+// fetches the next row into them): eval_dots is the only part that reads the plane itself.
+__device__ __forceinline__ void eval_dots(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, Bottom &g) {
     g.t0 = fma2(n0, bc(D.fl[0]), fma2(n1, bc(D.fl[1]), n2));
     g.t1 = fma2(n0, bc(D.fm[0]), fma2(n1, bc(D.fm[1]), n2));
     g.t2 = fma2(n0, bc(D.fr[0]), fma2(n1, bc(D.fr[1]), n2));
     g.ad = abs2(d4);
+}
+
+template <bool kMergedRcp, bool kMargin>
+__device__ __forceinline__ void eval_bottom_rest(const DetConst &D, Bottom &g) {
     f2 i0, i1;
     if (kMergedRcp) {
         // 1/t_l and 1/t_m from one MUFU.RCP.  Only used once max-votes is known to be 6, where a degenerate
@@ -235,6 +240,12 @@ __device__ __forceinline__ void eval_bottom(const DetConst &D, f2 n0, f2 n1, f2 
     // |X_l - X_r|^2 from the difference itself (|a|^2 + |b|^2 - 2 a.b would cancel when X_l is close to X_r)
     const f2 c0 = sub2(g.a[0], g.b[0]), c1 = sub2(g.a[1], g.b[1]), c2 = sub2(g.a[2], g.b[2]);
     g.nc = fma2(c2, c2, fma2(c1, c1, mul2(c0, c0)));
+}
+
+template <bool kMergedRcp, bool kMargin>
+__device__ __forceinline__ void eval_bottom(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, Bottom &g) {
+    eval_dots(D, n0, n1, n2, d4, g);
+    eval_bottom_rest<kMergedRcp, kMargin>(D, g);
 }
 
 // kMargin: 0 = none, 1 = out.m = geometric margin + mc, 2 = geometric margin only (the caller accounts for mc).

@@ -1,0 +1,623 @@
+// Resident-database polling kernel of the packed fp32 modes (FAST, VERIFIED) -- the default since round 2.
+//
+// The ring kernels (gpp_poll2.cuh) stream the database through ONE tile ring per CTA, so the eight warps of a CTA
+// run at the pace of their slowest detection (~20 % of the warp time was spent waiting for the next tile).  Here no
+// two warps share anything:
+//   * one persistent CTA per SM; the first `resident_rows` rows (1 row = 32 plane pairs = 1 KB) of the
+//     pair-interleaved database are staged ONCE per CTA into shared memory by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier, SASS UBLKCP) -- up to 216 KB, i.e. 13.8k of the 21.6k planes of the largest shipped
+//     database, all of the smaller ones;
+//   * the remaining rows are read by each warp straight from L2 (the database never leaves L2), one row ahead of
+//     its use (register prefetch, ld.global.nc), so that the L2 latency hides behind the previous row's arithmetic;
+//   * every warp claims its own work items from a device counter.  An item is (detection, plane segment): large
+//     batches use one segment per detection, small batches cut every detection into up to 32 segments so that a
+//     single image still fills the 148 SMs; the warp that finishes the last segment of a detection merges the
+//     partial (max-votes, residual, index) results and runs the epilogue;
+//   * rows that repeat the previous row of their image (FilterDetections' -1 padding) are skipped when claimed; the
+//     warp that finishes a detection also writes its results to the identical rows that follow it.  One launch per
+//     call, no work lists, no memset: the counters are reset by the last warp / CTA that uses them.
+// The per-hypothesis arithmetic, the VERIFIED filter and the exact bookkeeping are those of gpp_poll2.cuh
+// (fit_road_planes.py:86-119); only the schedule and the data movement differ.
+#pragma once
+#include "gpp_poll2.cuh"
+
+namespace gpp {
+
+struct SegPartial {       // result of one plane segment of a detection
+    float r;
+    int M, idx, pad;
+};
+
+struct PollArgs3 {
+    const float *boxes, *dims, *pinv;
+    const int32_t *orient;
+    const u64 *pairs;            // pair-interleaved normalised DB (see PollArgs2)
+    const float4 *planes;        // plain normalised DB, for the exact paths
+    int n_planes, n_pairs_padded, dets_per_image;
+    long long n_det;
+    float *keypoints, *keyplanes, *residuals;
+    long long *best;
+    // schedule
+    int resident_rows;           // rows of `pairs` kept in shared memory (0 = stream everything from L2)
+    int n_seg, rows_per_seg;     // plane segments per detection
+    unsigned long long *claim;   // [0] work-item counter, [1] CTAs that have left; zero at launch, reset by the last CTA
+    SegPartial *partials;        // [n_det * n_seg]                      (n_seg > 1 only)
+    unsigned int *seg_arrived;   // [n_det], zero at launch, reset by the last segment of the detection
+    unsigned long long *seg_best;   // [n_det], shared (max-votes, best residual) key of a detection's segments, same life cycle
+};
+
+__device__ __forceinline__ Detection<ExactF32> load_det_exact(const float *detx) {
+    Detection<ExactF32> det;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        det.dl[i] = detx[i]; det.dm[i] = detx[3 + i]; det.dr[i] = detx[6 + i]; det.dt[i] = detx[9 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) det.td[i] = detx[12 + i];
+    return det;
+}
+
+// (max-votes, best residual) as one 64-bit key that grows when the pair improves: more votes first, then a smaller
+// residual (r >= +0, never NaN: the bit pattern orders like the value)
+__device__ __forceinline__ unsigned long long seg_key(int M, float r) {
+    return ((unsigned long long)(unsigned)(M + 1) << 32) | (unsigned long long)(0xffffffffu - __float_as_uint(r));
+}
+
+// Where a lane finds its pair of row r: shared memory for the resident rows, L2 (read-only path) for the others.
+// The scan loops keep ONE copy of the lane's 32 bytes in registers: as soon as the dot products of row r are
+// formed, the registers are refilled with row r + 1 (so the L2 / shared-memory latency hides behind the rest of
+// row r), and the few rows that get past the first filter stage read their pair again (an L1 / shared-memory hit).
+struct RowSource {
+    // loop-carried state (kept as running values so that the compiler has nothing to recompute per row)
+    uint32_t saddr;            // shared-memory address this lane's pair of the CURRENT row has / would have if resident
+    int rows_left;             // rows of the segment not yet polled, the current one included (warp-uniform)
+    int res_left;              // resident rows from the current one on (<= 0: the current row is streamed)
+    // constants
+    uint32_t sbase;            // shared-memory address of the resident rows
+    const unsigned char *gbase;   // global address of the pair database
+    __device__ __forceinline__ void init(uint32_t sbase_, const void *pairs, int res, int r_begin, int r_end, int lane) {
+        sbase = sbase_;
+        gbase = static_cast<const unsigned char *>(pairs);
+        saddr = sbase_ + (uint32_t(r_begin) << 10) + 32u * lane;
+        rows_left = r_end - r_begin;
+        res_left = res - r_begin;
+    }
+    __device__ __forceinline__ void load(bool resident, uint32_t addr, ulonglong2 &a, ulonglong2 &b) const {
+        if (resident) {
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a.x), "=l"(a.y) : "r"(addr));
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+16];" : "=l"(b.x), "=l"(b.y) : "r"(addr));
+        } else {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(gbase + (addr - sbase));
+            a = __ldg(p);
+            b = __ldg(p + 1);
+        }
+    }
+    __device__ __forceinline__ bool more() const { return rows_left > 1; }
+    __device__ __forceinline__ void load_next(ulonglong2 &a, ulonglong2 &b) const { load(res_left > 1, saddr + 1024u, a, b); }
+    __device__ __forceinline__ void load_again(ulonglong2 &a, ulonglong2 &b) const { load(res_left > 0, saddr, a, b); }
+    __device__ __forceinline__ void advance() {
+        saddr += 1024u;
+        --rows_left;
+        --res_left;
+    }
+    __device__ __forceinline__ int plane_index() const { return int((saddr - sbase) >> 4); }   // first plane of the lane's pair
+};
+
+// ------------------------------------------------------------------ VERIFIED: filter + exact bookkeeping of a warp
+// The body of the row function is the filter of poll2_kernel<..., kVMode = 1> (see the comments there and DESIGN.md
+// section 4.1): all-six phase in two stages, general phase with the order-statistic pre-test, early bounds from
+// certain planes, survivors queued and re-evaluated 32 at a time in the exact arithmetic.
+struct VerifiedScan {
+    LaneState<float> st;   // exact selection state of this lane (max-votes, best residual, index)
+    float wbest;           // warp-uniform: best EXACT residual so far at max-votes Mcur (or an early upper bound of it)
+    float wthr;            // (wbest + mc)(1 + 2^-18)
+    int qn;                // survivors waiting in the warp's queue (warp-uniform)
+    int Mcur;              // exact max-votes so far (warp-uniform)
+
+    __device__ __forceinline__ void begin() {
+        st.reset(FLT_MAX);
+        wbest = FLT_MAX;
+        wthr = __int_as_float(0x7f800000);
+        qn = 0;
+        Mcur = -1;
+    }
+
+    // adopt a bound found by another segment of the same detection (exact values, published through seg_best)
+    __device__ __forceinline__ void adopt(unsigned long long key, const DetConst &D) {
+        const int M = int(unsigned(key >> 32)) - 1;
+        const float r = __uint_as_float(0xffffffffu - unsigned(key & 0xffffffffu));
+        if (M > Mcur) {
+            Mcur = M;
+            wbest = r;
+            wthr = (wbest + D.mc) * 1.0000038f;
+        } else if (M == Mcur && r < wbest) {
+            wbest = r;
+            wthr = (wbest + D.mc) * 1.0000038f;
+        }
+    }
+
+    __device__ __forceinline__ void flush(const float *detx, const float4 *__restrict__ planes, const int *queue,
+                                          int lane, bool all, const DetConst &D) {
+        const Detection<ExactF32> det = load_det_exact(detx);
+        while (qn >= 32) {
+            qn -= 32;
+            verify_general(det, planes, queue[qn + lane], st);
+        }
+        if (all && qn > 0) {
+            if (lane < qn) verify_general(det, planes, queue[lane], st);
+            qn = 0;
+        }
+        __syncwarp();
+        const int Mnew = __reduce_max_sync(0xffffffffu, st.M);
+        const float wnew = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(st.M == Mnew ? st.bestR : FLT_MAX)));
+        if (Mnew > Mcur) {
+            Mcur = Mnew;
+            wbest = wnew;
+        } else if (Mnew == Mcur) {
+            wbest = fminf(wbest, wnew);       // early bounds (and adopted ones) stay valid at the same max-votes
+        }                                     // Mnew < Mcur: the bound was adopted from another segment, keep it
+        wthr = (wbest + D.mc) * 1.0000038f;
+    }
+
+    // One row: c0 / c1 hold this lane's pair of row r on entry and of row r + 1 (if `more`) on return.
+    __device__ __forceinline__ void row(const DetConst &D, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+                                        const int N, const int lane, int *queue, const float *detx,
+                                        const float4 *__restrict__ planes) {
+        PairResult h;
+        bool trig0, trig1, urgent = false;
+        Bottom g;
+        eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
+        if (src.more()) src.load_next(c0, c1);
+        if (Mcur == 6) {
+            // stage 1: the bottom face only
+            eval_bottom_rest<true, true>(D, g);
+            h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+            h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+            h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+            const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
+            {
+                const f2 Slo = fma2(neg2(g.w), bc(D.ms), S3);
+                if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) return;
+            }
+            // stage 2: X_t, the height and the two slanted edges, the full margin
+            ulonglong2 v0, v1;
+            src.load_again(v0, v1);
+            const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
+            f2 ne, nf;
+            eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+            h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+            h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+            const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
+            const f2 Rlo = sub2(R, h.m);
+            trig0 = !(lo(Rlo) > wthr);
+            trig1 = !(hi(Rlo) > wthr);
+            if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
+            h.m = add2(h.m, bc(D.mc));
+            finalize_margin(h, R, D);
+            const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                             rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+            const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
+            trig0 = trig0 && !(lo(rlo) > 0.7f);
+            trig1 = trig1 && !(hi(rlo) > 0.7f);
+            if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
+            h.finish_zc();
+            const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
+            const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
+            {
+                // a plane that CERTAINLY has six votes and passes the z-check bounds the final best residual
+                const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+                const f2 rhi = add2(rm, h.m);
+                const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+                const float e0 = (lo(rhi) <= 0.7f && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX) ? lo(Rhi) : FLT_MAX;
+                const float e1 = (hi(rhi) <= 0.7f && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX) ? hi(Rhi) : FLT_MAX;
+                const float e = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(e0, e1))));
+                if (e < wbest) {
+                    wbest = e;
+                    wthr = (wbest + D.mc) * 1.0000038f;
+                }
+            }
+            trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
+            trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
+        } else {
+            eval_bottom_rest<false, true>(D, g);
+            {
+                ulonglong2 v0, v1;
+                src.load_again(v0, v1);
+                f2 ne, nf;
+                eval_top<1, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), g, h, ne, nf);
+                h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+                h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+                h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+                h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+                h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+            }
+            const f2 R = resid_sum(h);
+            finalize_margin(h, R, D);
+            const f2 Rlo = sub2(R, h.m);
+            if (Mcur >= 4) {
+                const f2 p0 = pk(fmaxf(fabsf(lo(h.r[0])), fabsf(lo(h.r[1]))), fmaxf(fabsf(hi(h.r[0])), fabsf(hi(h.r[1]))));
+                const f2 p1 = pk(fmaxf(fabsf(lo(h.r[2])), fabsf(lo(h.r[3]))), fmaxf(fabsf(hi(h.r[2])), fabsf(hi(h.r[3]))));
+                const f2 p2 = pk(fmaxf(fabsf(lo(h.r[4])), fabsf(lo(h.r[5]))), fmaxf(fabsf(hi(h.r[4])), fabsf(hi(h.r[5]))));
+                const f2 pmax = pk(max3f(lo(p0), lo(p1), lo(p2)), max3f(hi(p0), hi(p1), hi(p2)));
+                const f2 pmin = pk(fminf(fminf(lo(p0), lo(p1)), lo(p2)), fminf(fminf(hi(p0), hi(p1)), hi(p2)));
+                const f2 pmed = pk(fmaxf(fminf(lo(p0), lo(p1)), fminf(fmaxf(lo(p0), lo(p1)), lo(p2))),
+                                   fmaxf(fminf(hi(p0), hi(p1)), fminf(fmaxf(hi(p0), hi(p1)), hi(p2))));
+                const f2 more = sub2(Mcur == 5 ? pmax : pmed, h.m);      // > 0.7: cannot have more votes
+                const f2 same = sub2(Mcur == 5 ? pmed : pmin, h.m);      // > 0.7: cannot have as many
+                const bool nan0 = !(lo(R) == lo(R)), nan1 = !(hi(R) == hi(R));   // degenerate: full test
+                const bool may0 = nan0 || !(lo(more) > 0.7f) || (!(lo(same) > 0.7f) && !(lo(Rlo) > wbest));
+                const bool may1 = nan1 || !(hi(more) > 0.7f) || (!(hi(same) > 0.7f) && !(hi(Rlo) > wbest));
+                if (!__any_sync(0xffffffffu, may0 || may1)) return;
+            }
+            h.finish_zc();
+            const f2 zhi = z_upper(h, D);
+            const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
+            const bool k0 = V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
+            const bool k1 = V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+            if (Mcur >= 4 && __any_sync(0xffffffffu, k0 || k1)) {
+                const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+                const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+                const bool c0 = k0 && strict_votes(h, false) == Mcur && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX;
+                const bool c1 = k1 && strict_votes(h, true) == Mcur && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX;
+                const float e = __uint_as_float(__reduce_min_sync(
+                    0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
+                wbest = fminf(wbest, e);
+            }
+            trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
+            trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
+            urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
+        }
+        const int j = src.plane_index();
+        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
+        const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
+        if (b0 | b1) {
+            const unsigned below = (1u << lane) - 1u;
+            if (q0) queue[qn + __popc(b0 & below)] = j;
+            qn += __popc(b0);
+            if (q1) queue[qn + __popc(b1 & below)] = j + 1;
+            qn += __popc(b1);
+            __syncwarp();
+            const bool flush_all = __any_sync(0xffffffffu, urgent);
+            if (qn >= 32 || flush_all) flush(detx, planes, queue, lane, flush_all, D);
+        }
+    }
+
+    // end of the segment: the last partial batch; afterwards `st` holds the exact result of the scanned planes
+    __device__ __forceinline__ void finish(const float *detx, const float4 *__restrict__ planes, const int *queue,
+                                           int lane) {
+        if (qn > 0) {
+            const Detection<ExactF32> det = load_det_exact(detx);
+            if (lane < qn) verify_general(det, planes, queue[lane], st);
+            qn = 0;
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx) const {
+        Mw = __reduce_max_sync(0xffffffffu, st.M);
+        rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
+        idx = st.bestIdx;
+    }
+};
+
+// ------------------------------------------------------------------ FAST: the search in the fast arithmetic alone
+struct FastScan {
+    LaneState<float> st;   // general mode (max votes not yet known to be 6)
+    LaneBest b6;           // once a plane with six votes has been seen
+    bool m6;
+    float wbest;
+
+    __device__ __forceinline__ void begin() {
+        st.reset(FLT_MAX);
+        b6.bestR = FLT_MAX;
+        b6.bestIdx = 0;
+        m6 = false;
+        wbest = FLT_MAX;
+    }
+    __device__ __forceinline__ void row(const DetConst &D, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1) {
+        PairResult h;
+        const int j = src.plane_index();
+        Bottom g;
+        eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
+        if (src.more()) src.load_next(c0, c1);
+        if (!m6) {
+            eval_bottom_rest<false, false>(D, g);
+            {
+                ulonglong2 v0, v1;
+                src.load_again(v0, v1);
+                f2 ne, nf;
+                eval_top<0, false>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), g, h, ne, nf);
+                h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+                h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+                h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+                h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+                h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+            }
+            const f2 R = resid_sum(h);
+            const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+            const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+            st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
+            st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
+            if ((src.rows_left & 3) == 0 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                m6 = true;                               // warp-uniform; candidates under a lower max are masked
+                b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
+                b6.bestIdx = st.bestIdx;
+                wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+            }
+            return;
+        }
+        // two stages like the VERIFIED all-six phase; the bottom-face sum never exceeds the full sum (rounded
+        // addition of non-negative terms is monotone), so leaving here decides what the full test would decide
+        eval_bottom_rest<true, false>(D, g);
+        h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+        h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+        h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+        {
+            const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
+            if (!__any_sync(0xffffffffu, !(lo(S3) > wbest) || !(hi(S3) > wbest))) return;
+        }
+        ulonglong2 v0, v1;
+        src.load_again(v0, v1);
+        const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
+        f2 ne, nf;
+        eval_top<0, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+        h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+        h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+        const f2 R = resid_sum(h);
+        if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
+            h.finish_zc();
+            b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])), lo(h.zc), lo(R), j);
+            b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])), hi(h.zc), hi(R), j + 1);
+            wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
+        }
+    }
+    __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx) const {
+        if (m6) {
+            Mw = 6;
+            rbest = b6.bestR;
+            idx = b6.bestIdx;
+        } else {
+            Mw = __reduce_max_sync(0xffffffffu, st.M);
+            rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
+            idx = st.bestIdx;
+        }
+    }
+};
+
+// rows m and n of the detection arrays hold the same bits (boxes 12 + dimensions 3 + orientation 1 words)
+__device__ __forceinline__ bool same_detection(const PollArgs3 &a, long long m, long long n, int lane) {
+    unsigned x = 0, y = 0;
+    if (lane < 12) {
+        x = __ldg(reinterpret_cast<const unsigned *>(a.boxes) + 12 * m + lane);
+        y = __ldg(reinterpret_cast<const unsigned *>(a.boxes) + 12 * n + lane);
+    } else if (lane < 15) {
+        x = __ldg(reinterpret_cast<const unsigned *>(a.dims) + 3 * m + (lane - 12));
+        y = __ldg(reinterpret_cast<const unsigned *>(a.dims) + 3 * n + (lane - 12));
+    } else if (lane == 15) {
+        x = (unsigned)__ldg(a.orient + m);
+        y = (unsigned)__ldg(a.orient + n);
+    }
+    return __all_sync(0xffffffffu, x == y);
+}
+
+constexpr int kWarpSmem3 = kVerifyQueue * (int)sizeof(int) + 20 * (int)sizeof(float);   // queue + exact constants
+__host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
+    return size_t(resident_rows) * 1024 + size_t(warps) * kWarpSmem3 + 16;
+}
+
+// kSeg: detections are cut into plane segments (small batches); the large-batch instantiation carries none of it
+template <int kWarps, int kVMode, bool kSeg>
+__global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 args) {
+    constexpr bool kVerified = kVMode != 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = args.n_planes;
+    const int NR = args.n_pairs_padded >> 5;                  // rows of 32 pairs
+    const int res = args.resident_rows;
+    unsigned char *warp_area = smem_raw + size_t(res) * 1024 + size_t(warp) * kWarpSmem3;
+    int *queue = reinterpret_cast<int *>(warp_area);
+    float *detx = reinterpret_cast<float *>(warp_area + kVerifyQueue * sizeof(int));
+    uint64_t *stage_bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(res) * 1024 + size_t(kWarps) * kWarpSmem3);
+
+    // ---- stage the resident rows: 1-D TMA bulk copies, one mbarrier for the lot
+    if (res > 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(stage_bar, 1);
+            mbar_fence_init();
+            const uint32_t total = uint32_t(res) * 1024u;
+            mbar_arrive_expect_tx(stage_bar, total);
+            for (uint32_t off = 0; off < total; off += 32768u) {
+                const uint32_t bytes = min(32768u, total - off);
+                tma_load_1d(smem_raw + off, reinterpret_cast<const unsigned char *>(args.pairs) + off, bytes, stage_bar);
+            }
+        }
+        __syncthreads();
+        mbar_wait(stage_bar, 0);             // every thread: nobody leaves or reads before the copies have landed
+    }
+
+    const int n_seg = kSeg ? args.n_seg : 1;
+    const unsigned long long n_items = (unsigned long long)args.n_det * (unsigned)n_seg;
+    unsigned long long next_claim = 0;
+    if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);
+    next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+
+    for (;;) {
+        const unsigned long long item = next_claim;
+        if (item >= n_items) break;                                  // warp-uniform: this warp retires
+        if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);     // claimed one item ahead
+        next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+        const long long m = kSeg ? (long long)(item / (unsigned)n_seg) : (long long)item;
+        const int seg = kSeg ? int(item - (unsigned long long)m * (unsigned)n_seg) : 0;
+        // a row that repeats the previous row of its image is written by the warp that polls that row
+        if ((m % args.dets_per_image) != 0 && same_detection(args, m, m - 1, lane)) continue;
+
+        // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
+        DetConst D;
+        {
+            Detection<ExactF32> det0;
+            load_detection<ExactF32, ExactF32>(det0, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
+                                               args.pinv + 12 * (m / args.dets_per_image));
+#pragma unroll
+            for (int i = 0; i < 6; ++i) D.td[i] = det0.td[i];
+            fast_constants(D, det0);
+            __syncwarp();                            // the previous item's readers are done
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    detx[i] = det0.dl[i]; detx[3 + i] = det0.dm[i]; detx[6 + i] = det0.dr[i]; detx[9 + i] = det0.dt[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) detx[12 + i] = det0.td[i];
+            }
+            __syncwarp();
+        }
+
+        const int r_begin = kSeg ? seg * args.rows_per_seg : 0;
+        const int r_end = kSeg ? min(NR, r_begin + args.rows_per_seg) : NR;
+        RowSource src;
+        src.init(smem_u32(smem_raw), args.pairs, res, r_begin, r_end, lane);
+        ulonglong2 c0, c1;
+        src.load_again(c0, c1);
+        int Mw, idx;
+        float rbest;
+        if (kVerified) {
+            VerifiedScan sc;
+            sc.begin();
+            for (; src.rows_left > 0; src.advance()) {
+                // segments of one detection share their bounds: the key is fetched here and used after the row
+                const bool share = kSeg && (src.rows_left & 3) == 0;
+                unsigned long long key = 0ull;
+                if (share) key = *reinterpret_cast<volatile unsigned long long *>(args.seg_best + m);
+                const int Mb = sc.Mcur;
+                const float wb = sc.wbest;
+                sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
+                if (kSeg && (sc.Mcur != Mb || sc.wbest < wb) && lane == 0)
+                    atomicMax(args.seg_best + m, seg_key(sc.Mcur, sc.wbest));
+                if (share) sc.adopt(key, D);
+            }
+            sc.finish(detx, args.planes, queue, lane);
+            sc.result(Mw, rbest, idx);
+        } else {
+            FastScan sc;
+            sc.begin();
+            for (; src.rows_left > 0; src.advance()) sc.row(D, src, c0, c1);
+            sc.result(Mw, rbest, idx);
+        }
+        rbest = warp_min_first(rbest, idx);
+
+        if (kSeg) {
+            // ---- hand the partial result in; the warp that completes the detection merges and continues
+            unsigned arrived = 0;
+            if (lane == 0) {
+                SegPartial p;
+                p.r = rbest; p.M = Mw; p.idx = idx; p.pad = 0;
+                __stcg(reinterpret_cast<int4 *>(args.partials + m * n_seg + seg),
+                       make_int4(__float_as_int(p.r), p.M, p.idx, 0));
+                __threadfence();
+                arrived = atomicAdd(args.seg_arrived + m, 1u);
+            }
+            arrived = __shfl_sync(0xffffffffu, arrived, 0);
+            if (arrived != unsigned(n_seg - 1)) continue;
+            __threadfence();
+            SegPartial p;
+            p.M = -1; p.r = FLT_MAX; p.idx = 0;
+            if (lane < n_seg) {
+                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(args.partials + m * n_seg + lane));
+                p.r = __int_as_float(raw.x); p.M = raw.y; p.idx = raw.z;
+            }
+            Mw = __reduce_max_sync(0xffffffffu, p.M);
+            rbest = (p.M == Mw) ? p.r : FLT_MAX;
+            idx = p.idx;
+            rbest = warp_min_first(rbest, idx);
+            if (lane == 0) {                          // leave the scratch as it was found
+                args.seg_arrived[m] = 0u;
+                args.seg_best[m] = 0ull;
+            }
+        }
+
+        // ---- epilogue: lazy first-masked search, exact recompute of the winner (fit_road_planes.py:116-137)
+        const Detection<ExactF32> det = load_det_exact(detx);
+        const bool have_cand = rbest < FLT_MAX;
+        bool sentinel = false;
+        if (!(rbest < 100.0f)) {
+            int first_masked = -1;
+            for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
+                const int p = p0 + lane;                         // pair index; the padded DB covers it
+                const ulonglong2 v0 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p);
+                const ulonglong2 v1 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p + 1);
+                int V0, V1;
+                bool z0, z1;
+                if (kVerified) {
+                    const f2 a01 = from_u64(v0.x), b01 = from_u64(v0.y), c01 = from_u64(v1.x), d01 = from_u64(v1.y);
+                    float Rx;
+                    exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V0, Rx, z0);
+                    exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V1, Rx, z1);
+                } else {
+                    PairResult h;
+                    eval_pair<false>(PackFast(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                    V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                    z0 = lo(h.zc) < 0.0f;
+                    z1 = hi(h.zc) < 0.0f;
+                }
+                const bool mk0 = (2 * p < N) && ((V0 < Mw) || z0);
+                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || z1);
+                const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
+                if (b0 | b1) {
+                    const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
+                    const int f1 = b1 ? 2 * (p0 + __ffs(b1) - 1) + 1 : 0x7fffffff;
+                    first_masked = min(f0, f1);
+                }
+            }
+            if (first_masked >= 0) {
+                if (!have_cand || 100.0f < rbest || (100.0f == rbest && first_masked < idx)) {
+                    sentinel = true;
+                    idx = first_masked;
+                }
+            } else if (!have_cand) {
+                idx = 0;
+            }
+        }
+        // the winner in the exact arithmetic (every lane computes the same values; lane k keeps output word k)
+        float word = 0.0f;
+        {
+            const float4 pl = __ldg(args.planes + idx);
+            float X[4][3];
+            int V; float R; bool zneg;
+            hypothesis<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            const float rr = __fdiv_rn(sentinel ? 100.0f : R, 6.0f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) word = (lane == 3 * k + i) ? X[k][i] : word;
+            word = (lane == 12) ? pl.x : word;
+            word = (lane == 13) ? pl.y : word;
+            word = (lane == 14) ? pl.z : word;
+            word = (lane == 15) ? pl.w : word;
+            word = (lane == 16) ? rr : word;
+            // this row and the identical rows that follow it in the image
+            long long n = m;
+            do {
+                if (lane < 12) args.keypoints[12 * n + lane] = word;
+                else if (lane < 16) args.keyplanes[4 * n + (lane - 12)] = word;
+                else if (lane == 16) args.residuals[n] = word;
+                else if (lane == 17 && args.best) args.best[n] = idx;
+                ++n;
+            } while (n < args.n_det && (n % args.dets_per_image) != 0 && same_detection(args, n, m, lane));
+        }
+    }
+
+    // ---- the last CTA to leave resets the counters for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long left = atomicAdd(args.claim + 1, 1ull);
+        if (left == gridDim.x - 1) {
+            args.claim[0] = 0ull;
+            args.claim[1] = 0ull;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace gpp

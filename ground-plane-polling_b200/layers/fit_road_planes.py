@@ -222,6 +222,24 @@ class PlanePoller(object):
         _lib.check(self._lib.gpp_debug_set_config(self._h, int(variant), int(ctas_per_sm)),
                    'gpp_debug_set_config')
 
+    def debug_set_schedule(self, n_seg=0, resident_rows=-1):
+        """Test / tuning hook of the resident-database kernel: plane segments per detection (0 = automatic) and rows
+        of 64 planes kept in shared memory (-1 = automatic, 0 = stream everything from L2)."""
+        _lib.check(self._lib.gpp_debug_set_schedule(self._h, int(n_seg), int(resident_rows)),
+                   'gpp_debug_set_schedule')
+
+    # ------------------------------------------------------------------ runtime audit of the VERIFIED mode
+    def audit_set(self, every):
+        """Re-poll every ``every``-th detection of each 'verified' call in the EXACT arithmetic on the device and
+        count disagreements (0 = off; the environment variable GPP_AUDIT=n does the same for new handles)."""
+        _lib.check(self._lib.gpp_audit_set(self._h, int(every)), 'gpp_audit_set')
+
+    def audit_counts(self):
+        """(rows checked, rows whose plane index or residual differed) since the handle was created."""
+        checked, bad = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._lib.gpp_audit_counts(self._h, ctypes.byref(checked), ctypes.byref(bad)), 'gpp_audit_counts')
+        return int(checked.value), int(bad.value)
+
 
 _POLLERS = {}
 _POLLERS_LOCK = threading.Lock()

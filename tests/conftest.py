@@ -15,6 +15,25 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')
 
 
+def _have_b200():
+    try:
+        import torch
+        return torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a B200 runs the CPU suite and reports the GPU tests as skipped
+    (libgpp has no CPU fallback, so they could only fail in gpp_create)."""
+    if _have_b200():
+        return
+    skip = pytest.mark.skip(reason='needs a B200 (sm_100) device; libgpp has no CPU fallback')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 def load_planes(tag):
     return np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_%s.npy' % tag))
 

@@ -9,8 +9,8 @@ import pytest
 from conftest import ROOT
 
 
-def _declared_symbols():
-    with open(os.path.join(ROOT, 'include', 'gpp.h')) as f:
+def _declared_symbols(header='gpp.h'):
+    with open(os.path.join(ROOT, 'include', header)) as f:
         text = f.read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     return sorted(set(re.findall(r'\b(gpp_[a-z0-9_]+)\s*\(', text)))
@@ -25,10 +25,23 @@ def test_header_declares_the_expected_surface():
 
 def test_library_exports_every_declared_symbol(gpp):
     lib = gpp._lib.load()
-    for name in _declared_symbols():
+    declared = _declared_symbols('gpp.h') + _declared_symbols('gpp_debug.h')
+    for name in declared:
         assert hasattr(lib, name), 'libgpp.so does not export %s' % name
         assert name in gpp._lib.SIGNATURES, 'no ctypes signature for %s' % name
+    assert sorted(gpp._lib.SIGNATURES) == sorted(set(declared)), 'ctypes signatures without a declaration'
     assert lib.gpp_version() == 100
+
+
+def test_debug_hooks_are_not_part_of_the_drop_in_header():
+    """Measurement / tuning / test hooks live in include/gpp_debug.h; the boundary header holds only what a caller
+    of fit_road_planes and its neighbouring steps binds."""
+    public = _declared_symbols('gpp.h')
+    assert not [s for s in public if s.startswith(('gpp_debug_', 'gpp_microbench', 'gpp_audit_'))]
+    dbg = _declared_symbols('gpp_debug.h')
+    for must in ('gpp_microbench', 'gpp_debug_set_config', 'gpp_debug_scores', 'gpp_debug_set_schedule',
+                 'gpp_audit_set', 'gpp_audit_counts'):
+        assert must in dbg
 
 
 def test_library_is_in_tree_and_sm100a(gpp):

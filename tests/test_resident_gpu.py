@@ -1,0 +1,121 @@
+"""GPU: the resident-database kernel (csrc/gpp_poll3.cuh, default of the 'verified' and 'fast' modes) under every
+schedule it can take -- detections cut into plane segments, the database resident in shared memory / streamed from
+L2 / half and half, rows that repeat the previous row written by the warp that polled the first of them -- must
+return what the oracle returns, bit for bit ('verified') or up to rounding-noise ties ('fast')."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, load_planes
+from gpp_b200.utils import synthetic
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, want):
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and g.dtype == w.dtype
+        assert np.array_equal(g, w, equal_nan=True)
+
+
+def _hard_batch(planes, seed=77):
+    """padding rows, runs of identical rows inside an image, detections without six votes, noisy key-points"""
+    boxes, dims, orient, P_inv = synthetic.synth_detections(5, 48, planes, seed=seed, n_valid=37, kp_noise_px=3.0)
+    boxes, dims, orient = boxes.copy(), dims.copy(), orient.copy()
+    dims[1, :9, 1] *= 1.7                                   # max-votes < 6
+    for b, (lo, hi) in ((2, (5, 11)), (3, (0, 4)), (4, (20, 21))):        # identical rows in the middle / at the start
+        boxes[b, lo:hi], dims[b, lo:hi], orient[b, lo:hi] = boxes[b, lo], dims[b, lo], orient[b, lo]
+    boxes[0, 47], dims[0, 47], orient[0, 47] = boxes[1, 0], dims[1, 0], orient[1, 0]   # equal rows in DIFFERENT images
+    return boxes, dims, orient, P_inv
+
+
+@pytest.mark.parametrize('n_seg,resident', [(1, 0), (1, 3), (1, -1), (2, -1), (5, 0), (7, 11), (32, -1), (32, 0)])
+def test_every_schedule_equals_the_oracle(gpp, poller, n_seg, resident):
+    planes = load_planes('10k')[:7001]                     # ragged last row, duplicate planes of the 10k database
+    boxes, dims, orient, P_inv = _hard_batch(planes)
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    poller.debug_set_schedule(n_seg, resident)
+    try:
+        got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
+        fast = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='fast', return_index=True)
+        few = gpp.fit_road_planes(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes, mode='verified',
+                                  return_index=True)
+    finally:
+        poller.debug_set_schedule(0, -1)
+    _same(got, want)
+    _same(few, c_oracle.fit_road_planes_c(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes,
+                                          return_index=True))
+    valid = orient >= 0                      # padding rows are degenerate: pure rounding-noise ties
+    assert np.mean(fast[3][valid] == want[3][valid]) > 0.97
+
+
+@pytest.mark.parametrize('name', golden_cases())
+@pytest.mark.parametrize('n_seg', [3, 32])
+def test_segmented_schedule_on_the_golden_vectors(gpp, poller, name, n_seg):
+    """sentinel-100 winners, NaN planes, all-masked rows, per-image databases: the merge of the segments' partial
+    results must keep every selection rule (max votes over ALL planes, lowest index on ties)"""
+    g = load_golden(name)
+    poller.debug_set_schedule(n_seg, 1)
+    try:
+        got = gpp.fit_road_planes(g['boxes'], g['dimensions'], g['orientations'], g['P_inv'], g['planes_raw'],
+                                  mode='verified')
+    finally:
+        poller.debug_set_schedule(0, -1)
+    _same(got, [g['keypoints'], g['keyplanes'], g['residuals']])
+
+
+def test_repeated_calls_leave_the_counters_clean(gpp, poller):
+    """the kernel resets its own claim / segment counters: many back-to-back calls of different shapes on one handle"""
+    planes = load_planes('1k')
+    rng = np.random.default_rng(5)
+    for it in range(12):
+        B, D = int(rng.integers(1, 5)), int(rng.integers(1, 60))
+        boxes, dims, orient, P_inv = synthetic.synth_detections(B, D, planes, seed=100 + it, n_valid=max(1, D - 3))
+        want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+        poller.debug_set_schedule(int(rng.integers(0, 9)), int(rng.integers(-1, 9)))
+        try:
+            got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
+        finally:
+            poller.debug_set_schedule(0, -1)
+        _same(got, want)
+
+
+def test_large_batch_resident_equals_ring_kernel(gpp, poller):
+    """automatic schedule of a large batch (one segment, 216 resident rows + streamed rest) against the round-1 ring
+    kernel and the EXACT kernel on 300 images x 100 rows x 21634 planes"""
+    import torch
+    planes = load_planes('22k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(300, 100, planes, seed=9, n_valid=93)
+    dev = torch.device('cuda', 0)
+    args = [torch.from_numpy(a).to(dev) for a in (boxes, dims, orient, P_inv.astype(np.float32))]
+    new = gpp.fit_road_planes_torch(*args, planes, mode='verified', return_index=True)
+    ex = gpp.fit_road_planes_torch(*args, planes, mode='exact', return_index=True)
+    poller.debug_set_config(204, 0)
+    try:
+        old = gpp.fit_road_planes_torch(*args, planes, mode='verified', return_index=True)
+    finally:
+        poller.debug_set_config(0, 0)
+    torch.cuda.synchronize()
+    for a, b, c in zip(new, old, ex):
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(a.cpu().numpy(), c.cpu().numpy(), equal_nan=True)
+
+
+def test_runtime_audit_counts(gpp, poller):
+    """gpp_audit_set: every n-th detection of a 'verified' call is re-polled by the EXACT kernel on the device"""
+    planes = load_planes('10k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(7, 100, planes, seed=21, n_valid=90)
+    c0, b0 = poller.audit_counts()
+    poller.audit_set(3)
+    try:
+        got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
+        again = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified')       # without an index array
+    finally:
+        poller.audit_set(0)
+    c1, b1 = poller.audit_counts()
+    assert c1 - c0 == 2 * ((700 + 2) // 3) and b1 == b0
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    _same(got, want)
+    _same(again, want[:3])
+    gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified')                  # audit off again
+    assert poller.audit_counts() == (c1, b1)
