@@ -22,6 +22,6 @@ from .utils import pose  # noqa: F401
 from .utils.pose import recover_pose, recover_pose_torch  # noqa: F401
 from .utils import calibration, kitti  # noqa: F401
 from .utils.calibration import load_calibration, load_road_planes  # noqa: F401
-from .utils.kitti import kitti_records, postprocess_image, select_detections  # noqa: F401
+from .utils.kitti import image_detections, kitti_records, postprocess_image, select_detections  # noqa: F401
 
 __version__ = '0.1.0'

@@ -11,7 +11,7 @@ from .. import _lib
 from ..layers.fit_road_planes import get_poller
 from .pose import recover_pose
 
-__all__ = ['select_detections', 'kitti_records', 'format_kitti_lines', 'postprocess_image']
+__all__ = ['select_detections', 'kitti_records', 'format_kitti_lines', 'postprocess_image', 'image_detections']
 
 
 def select_detections(scores, score_threshold=0.05, max_detections=100):
@@ -68,3 +68,22 @@ def postprocess_image(boxes, dimensions, scores, labels, orientations, keypoints
             'scores': np.asarray(scores)[keep], 'locations': locations, 'angles': angles, 'dimensions': dims_out,
             'residuals': np.asarray(residuals)[keep], 'orientations': orient,
             'keyplanes': np.asarray(keyplanes).reshape(-1, 4)[keep], 'kitti': records}
+
+
+def image_detections(boxes, dimensions, scores, labels, orientations, keypoints, keyplanes, score_threshold=0.05,
+                     max_detections=100):
+    """The per-image detection table of the reference's second caller (utils/eval.py:96-118, `_get_detections`):
+    rows kept by the score filter in decreasing-score order, columns = 12 box values, 3 dimensions, score, the four
+    polled 3-D key-points flattened to 12, the 4 key-plane parameters, orientation, label (34 columns).  Inputs are
+    the (1, 100, ...) arrays the inference model returns -- ``keypoints`` (1, D, 4, 3) and ``keyplanes`` (1, D, 1, 4)
+    exactly as ``fit_road_planes`` returns them."""
+    scores = np.asarray(scores)
+    keep = select_detections(scores[0], score_threshold, max_detections)
+    plane_pts = np.asarray(keypoints)[0, keep, :, :]
+    plane_pts = np.reshape(plane_pts, (plane_pts.shape[0], 12))
+    planes = np.asarray(keyplanes)[0, keep, :, :]
+    planes = np.reshape(planes, (planes.shape[0], 4))
+    return np.concatenate([np.asarray(boxes)[0, keep, :], np.asarray(dimensions)[0, keep, :],
+                           np.expand_dims(scores[0][keep], axis=1), plane_pts, planes,
+                           np.expand_dims(np.asarray(orientations)[0, keep], axis=1),
+                           np.expand_dims(np.asarray(labels)[0, keep], axis=1)], axis=1)

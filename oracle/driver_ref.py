@@ -8,8 +8,9 @@ from /root/reference/keras_retinanet_3D/bin/run_network.py:110-326 as one chain 
         -> outputs dict of the .mat file                                      (:291)
         -> KITTI text lines                                                   (:295-326)
 
-Pinning: every link is pinned separately (tests/golden/*.npz); the selection / formatting lines are restated
-verbatim here.  The image utilities and the anchors are pinned by tests/golden/driver_utils.npz
+Pinning: every link is pinned separately (tests/golden/*.npz), and the selection / pose / outputs / KITTI-line part
+(driver_image_ref) equals, bit for bit and character for character, what the reference's own lines :113-330 produce
+when they are cut out of run_network.py and exec'd (tests/golden/pose_*.npz, tests/test_pose_oracle_golden.py).  The image utilities and the anchors are pinned by tests/golden/driver_utils.npz
 (make_golden_driver.py runs the reference's own utils/anchors.py and utils/image.py).
 """
 import numpy as np

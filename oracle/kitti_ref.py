@@ -1,7 +1,9 @@
 """
 ORACLE (test infrastructure, NOT product code) -- restatement of the KITTI-record arithmetic of
 /root/reference/keras_retinanet_3D/bin/run_network.py:297-323 (numpy + cv2.Rodrigues like the reference).
-Parity status: no reference test exists for it; tolerance against the CUDA path 1e-4 (north_star).
+Parity status: PINNED -- equal, bit for bit, to (alpha, h, Y, r_y) as the reference's own writer lines compute them
+(tests/golden/pose_*.npz `kitti_rec`, made by exec'ing :298-327; tests/test_pose_oracle_golden.py).  Tolerance against
+the CUDA path 1e-4 (north_star).
 """
 import numpy as np
 

@@ -4,8 +4,9 @@ ORACLE (test infrastructure, NOT product code) -- restatement of the 6-DoF pose 
 the reference).  Only the branches that loop can reach are restated: ``outlier`` is 2 for orientation 0/3
 and 0 for orientation 1/2 (:147-150), so orientation 1 -> :167-177, 2 -> :178-188, 0 -> :204-214,
 3 -> :237-247; the other branches (:156-166, :189-199, :215-236, :248-287) are dead code.
-Parity status: the reference has no test for this loop; cv2 is present here, so the oracle calls the very
-same cv2.Rodrigues.  Tolerance against the CUDA path: 1e-4 relative (BASELINE.json north_star).
+Parity status: PINNED -- tests/golden/pose_*.npz hold what the reference's own lines (:137-287, cut out of the file and
+exec'd by tests/golden/make_golden_pose.py) produce, and this restatement equals them bit for bit
+(tests/test_pose_oracle_golden.py).  Tolerance against the CUDA path: 1e-4 relative (BASELINE.json north_star).
 """
 import numpy as np
 

@@ -39,7 +39,7 @@ def load_planes(tag):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('detect_', 'driver_')))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('detect_', 'driver_', 'pose_')))
 
 
 def load_golden(name):

@@ -1,5 +1,5 @@
 """
-Generates tests/golden/pose_*.npz and driver_select_*.npz by EXECUTING the reference driver's own source lines (run in
+Generates tests/golden/pose_*.npz and driver_calib.npz by EXECUTING the reference driver's own source lines (run in
 the build container, where /root/reference exists; the GPU box only sees the committed vectors).
 
 /root/reference/keras_retinanet_3D/bin/run_network.py cannot be imported (it imports keras / tensorflow at the top),
@@ -12,12 +12,13 @@ the network outputs -- no line of them is retyped here:
   :137-287   the 6-DoF pose loop (all branches as written, dead ones included)   -> locations, angles, dimensions
   :291       the `outputs` dict of the .mat file                                 -> out_*
   :295-330   the KITTI writer (Rodrigues -> 8 corners -> Y / h / r_y / alpha, the text line)  -> kitti_lines, kitti_rec
-  utils/eval.py:94-116   the second caller's selection + reshape contract        -> eval_detections
+  utils/eval.py:96-118   the second caller's selection + reshape contract        -> eval_detections
 
 Cases: `pose_main` (3 images worth of polled detections, all four orientation classes, padding rows below the score
 threshold), `pose_identity` (detections whose axes are almost the camera axes: the small-angle branch of
 cv2.Rodrigues, incl. an exactly axis-aligned box), `pose_flip` (rotations by ~pi, the other special case),
-`pose_ties` (equal scores: argsort order), `pose_empty` (no score above the threshold).
+`pose_yaw` (pure yaw sweeps over (-pi, pi) and random rotations: r_y / alpha wrapping), `pose_main1` also has equal
+scores (argsort order), `pose_empty` (no score above the threshold).
 """
 import os
 import sys
@@ -40,11 +41,6 @@ def ref_lines(path, first, last):
     with open(path) as f:
         lines = f.readlines()
     return textwrap.dedent(''.join(lines[first - 1:last]))
-
-
-class _Capture(object):
-    """stands in for the KITTI writer's per-line locals: the exec'd writer block is instrumented by NOTHING; the
-    numbers it formats are recovered from a second exec of the same lines with f.write replaced by a recorder"""
 
 
 def run_reference_driver_lines(outs, scale, P, image_hw):
@@ -83,7 +79,7 @@ def run_reference_driver_lines(outs, scale, P, image_hw):
 
 
 def run_reference_eval_lines(outs):
-    """utils/eval.py:94-116: selection + reshape contract of the second caller (`_get_detections`)."""
+    """utils/eval.py:96-118: selection + reshape contract of the second caller (`_get_detections`)."""
     boxes, dimensions, scores, labels, orientations, plane_pts, planes, residuals = [np.array(o, copy=True) for o in outs]
     ns = {'np': np, 'boxes': boxes, 'dimensions': dimensions, 'scores': scores, 'labels': labels,
           'orientations': orientations, 'plane_pts': plane_pts, 'planes': planes, 'residuals': residuals,
@@ -102,7 +98,7 @@ def polled_case(seed, n_img, planes_tag, n_valid, rng):
     planes = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_%s.npy' % planes_tag))
     boxes, dims, orient, P_inv = synthetic.synth_detections(n_img, 100, planes, seed=seed, n_valid=n_valid)
     kp, kpl, res = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes)
-    return boxes, dims, orient, kp, kpl, res
+    return boxes, dims, orient, kp, kpl, res, P_inv
 
 
 def outs_for_image(b, boxes, dims, orient, kp, kpl, res, scores):
@@ -180,8 +176,10 @@ def main():
                         P=P_ref, P_inv=P_inv_ref)
 
     cases = {}
-    boxes, dims, orient, kp, kpl, res = polled_case(301, 3, '1k', 83, rng)
+    boxes, dims, orient, kp, kpl, res, P_inv = polled_case(301, 3, '1k', 83, rng)
+    extra = {}
     for b in range(3):
+        extra['pose_main%d' % b] = {'poll_P_inv': P_inv[b:b + 1], 'poll_planes_db': np.array('1k')}
         scores = np.where(np.arange(100) < 83, rng.uniform(0.0, 1.0, 100), -1.0).astype(np.float32)
         if b == 1:
             scores[5:9] = scores[5]                        # equal scores: argsort order of the reference
@@ -215,6 +213,7 @@ def main():
         rec_d['eval_detections'] = det
         rec_d['scale'] = np.float64(scale)
         rec_d['P_scaled'] = P_scaled
+        rec_d.update(extra.get(name, {}))
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **rec_d)
         print('%-14s kept %3d rows, %d KITTI lines, eval.py lines %d-%d' % (name, len(outputs['scores']), len(lines),
                                                                           eval_lines[0], eval_lines[1]))

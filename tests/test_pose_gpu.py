@@ -1,8 +1,11 @@
-"""GPU: pose recovery kernel against the restated reference loop (oracle/pose_ref.py, cv2.Rodrigues)."""
+"""GPU: pose recovery / KITTI-record kernels against the reference driver's own lines (tests/golden/pose_*.npz, made by
+exec'ing run_network.py:113-330) and against the restated loop (oracle/pose_ref.py, pinned to the same vectors)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import load_planes
+from conftest import GOLDEN, load_planes
 from gpp_b200.utils import synthetic
 from oracle import c_oracle
 from oracle.pose_ref import kitti_yaw, pose_ref
@@ -114,3 +117,83 @@ def test_return_pose_extension(gpp):
     assert len(t) == 6
     for a, b in zip(t[3:], full[4:]):
         assert np.array_equal(a.cpu().numpy(), b, equal_nan=True)
+
+
+POSE_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith('pose_') and f.endswith('.npz'))
+
+
+def _rot(rv):
+    import cv2
+    return np.stack([cv2.Rodrigues(np.asarray(v, np.float64))[0] for v in rv]) if len(rv) else np.zeros((0, 3, 3))
+
+
+@pytest.mark.parametrize('name', POSE_CASES)
+def test_pose_and_kitti_kernels_equal_the_reference_lines(gpp, name):
+    """locations, dimensions and yaw within 1e-4 relative (north_star) of what run_network.py:137-287 / :297-327
+    themselves compute -- all four orientation branches, near-identity and near-pi rotations"""
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    kp, dims, orient = g['select_keypoints'], g['select_dimensions'], g['select_orientations']
+    loc, ang, dout = gpp.recover_pose(kp, dims, orient)
+    wloc, wang, wdim = g['out_locations'], g['out_angles'], g['out_dimensions']
+    assert loc.shape == wloc.shape and ang.shape == wang.shape and dout.shape == wdim.shape
+    if len(kp) == 0:
+        return
+    scale = np.maximum(np.abs(wloc).max(axis=1, keepdims=True), 1.0)
+    assert np.all(np.abs(loc - wloc) <= RTOL * scale)
+    assert np.allclose(dout, wdim, rtol=RTOL, atol=0)
+    # the Rodrigues vector as a rotation (near pi the vector may flip sign: same rotation), then the KITTI yaw
+    assert np.abs(_rot(ang) - _rot(wang)).max() <= 2e-4
+    near_pi = np.linalg.norm(wang, axis=1) > np.pi - 2e-3
+    assert np.all(np.abs(ang[~near_pi] - wang[~near_pi]) <= RTOL * np.maximum(1.0, np.abs(wang[~near_pi]).max(1, keepdims=True)))
+    assert np.all(np.abs(_wrap(kitti_yaw(ang[~near_pi]) - kitti_yaw(wang[~near_pi]))) <= RTOL * np.pi)
+    rec = gpp.kitti_records(wloc, wang, wdim)
+    want = g['kitti_rec']
+    assert np.all(np.abs(_wrap(rec[:, 0] - want[:, 0])) <= RTOL * np.pi)
+    assert np.all(np.abs(_wrap(rec[:, 3] - want[:, 3])) <= RTOL * np.pi)
+    assert np.allclose(rec[:, 1], want[:, 1], rtol=RTOL, atol=1e-5)
+    assert np.allclose(rec[:, 2], want[:, 2], rtol=RTOL, atol=1e-4)
+
+
+@pytest.mark.parametrize('name', POSE_CASES)
+def test_postprocess_image_equals_the_reference_driver(gpp, name):
+    """one image through the product's driver tail (selection, unscale, pose, KITTI lines) against the reference's
+    `outputs` dict (:291) and the text its KITTI writer produced (:295-330)"""
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    out = gpp.postprocess_image(g['in_boxes'][0], g['in_dimensions'][0], g['in_scores'][0], g['in_labels'][0],
+                                g['in_orientations'][0], g['in_keypoints'][0], g['in_keyplanes'][0],
+                                g['in_residuals'][0], float(g['scale']))
+    for k in ('boxes', 'keypoints', 'labels', 'scores', 'residuals'):
+        assert np.array_equal(out[k], g['out_' + k]), k                     # selection / unscale: exact
+    n = len(out['scores'])
+    if n == 0:
+        return
+    assert np.allclose(out['locations'], g['out_locations'], rtol=RTOL, atol=1e-4)
+    assert np.allclose(out['dimensions'], g['out_dimensions'], rtol=RTOL, atol=0)
+    lines = gpp.kitti.format_kitti_lines(out['boxes'], out['dimensions'], out['locations'], out['scores'],
+                                         out['kitti'], (1242, 375))
+    want_lines = str(g['kitti_lines']).splitlines()
+    assert len(lines) == len(want_lines) == n
+    near_pi = np.linalg.norm(g['out_angles'], axis=1) > np.pi - 2e-3
+    for a, b, skip in zip(lines, want_lines, near_pi):
+        fa, fb = a.split(), b.split()
+        assert fa[:3] == fb[:3] == ['Car', '-1', '-1']
+        va, vb = np.array(fa[3:], dtype=np.float64), np.array(fb[3:], dtype=np.float64)
+        if skip:
+            continue
+        d = np.abs(va - vb)
+        d[[0, 11]] = np.abs(_wrap(d[[0, 11]]))                              # alpha, r_y live on the circle
+        assert np.all(d <= 0.0100001 + 1e-4 * np.abs(vb))                   # one unit of the last printed place
+
+
+def test_polled_keypoints_feed_the_second_caller(gpp):
+    """utils/eval.py:96-118 (`_get_detections`): the GPU path's (1, 100, 4, 3) / (1, 100, 1, 4) outputs go through the
+    reshapes of the second caller and give the reference's 34-column table bit for bit"""
+    g = dict(np.load(os.path.join(GOLDEN, 'pose_main1.npz')))
+    planes = load_planes(str(g['poll_planes_db']))
+    kp, kpl, res = gpp.fit_road_planes(g['in_boxes'], g['in_dimensions'], g['in_orientations'], g['poll_P_inv'],
+                                       np.expand_dims(planes, axis=0))          # the callers' (1, N, 4) feed
+    assert np.array_equal(kp, g['in_keypoints']) and np.array_equal(kpl, g['in_keyplanes'])
+    assert np.array_equal(res, g['in_residuals'])
+    det = gpp.image_detections(g['in_boxes'], g['in_dimensions'], g['in_scores'], g['in_labels'], g['in_orientations'],
+                               kp, kpl)
+    assert np.array_equal(det, g['eval_detections'], equal_nan=True)
