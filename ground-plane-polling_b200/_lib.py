@@ -26,6 +26,7 @@ SIGNATURES = {
     'gpp_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     'gpp_destroy': (c_int, [c_void_p]),
     'gpp_set_planes': (c_int, [c_void_p, c_void_p, c_int]),
+    'gpp_set_planes_raw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
     'gpp_set_planes_device': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'gpp_num_planes': (c_int, [c_void_p]),
     'gpp_get_normalised_planes': (c_int, [c_void_p, c_void_p]),

@@ -72,28 +72,6 @@ __global__ void normalise_planes_kernel(const float *__restrict__ raw, int n, ty
     out[j] = o;
 }
 
-// 64-bit content hash of the database as the caller passes it (callers re-feed the same 346 KB with every image:
-// four independent multiply chains keep this at a few microseconds)
-static uint64_t content_hash(const void *data, size_t bytes) {
-    const unsigned char *p = static_cast<const unsigned char *>(data);
-    const uint64_t k = 0xD6E8FEB86659FD93ull;
-    uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ (uint64_t)bytes, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull,
-                     0x27D4EB2F165667C5ull};
-    size_t i = 0;
-    for (; i + 32 <= bytes; i += 32) {
-        uint64_t x[4];
-        memcpy(x, p + i, 32);
-        for (int l = 0; l < 4; ++l) {
-            h[l] = (h[l] ^ x[l]) * k;
-            h[l] ^= h[l] >> 32;
-        }
-    }
-    uint64_t r = h[0];
-    for (int l = 1; l < 4; ++l) r = (r ^ h[l]) * k, r ^= r >> 29;
-    for (; i < bytes; ++i) r = (r ^ p[i]) * 0x100000001B3ull;
-    return r;
-}
-
 // ---------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -181,6 +159,7 @@ int gpp_destroy(gpp_handle *h) {
         cudaEventDestroy(p.first);
         cudaEventDestroy(p.second);
     }
+    if (h->planes_ready) cudaEventDestroy(h->planes_ready);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     delete h;
@@ -218,39 +197,77 @@ static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
     return gpp::build_pairs(h, s);
 }
 
-int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes) {
-    if (!h || !planes || n_planes <= 0) return set_error(GPP_EINVAL, "gpp_set_planes: bad argument");
-    const size_t bytes = sizeof(float) * 4 * (size_t)n_planes;
-    const uint64_t hash = content_hash(planes, bytes);
-    if (h->n_planes == n_planes && h->planes_hash == hash && h->planes_hash_valid) return GPP_OK;
+// every launch that may still read the resident database has an event on record: wait for them on `s`
+static int wait_for_fits(gpp_handle *h, cudaStream_t s) {
+    for (auto &w : h->slot3)
+        if (w.used) GPP_CUDA(cudaStreamWaitEvent(s, w.done, 0));
+    for (auto &w : h->work)
+        if (w.used) GPP_CUDA(cudaStreamWaitEvent(s, w.done, 0));
+    if (h->audit_used) GPP_CUDA(cudaStreamWaitEvent(s, h->audit_done, 0));
+    return GPP_OK;
+}
+
+int gpp_set_planes_raw(gpp_handle *h, const void *planes, int n_planes, int dtype, int order) {
+    if (!h || !planes || n_planes <= 0 || dtype < 0 || dtype > 1 || order < 0 || order > 1)
+        return set_error(GPP_EINVAL, "gpp_set_planes_raw: bad argument");
+    const size_t esz = dtype ? sizeof(double) : sizeof(float);
+    const size_t bytes = esz * 4 * (size_t)n_planes;
+    // The reference's callers re-feed the same database with every image: compare with the bytes of the last upload
+    // (exact, at memcmp speed) instead of converting / hashing / uploading again.
+    if (h->raw_valid && h->n_planes == n_planes && h->raw_dtype == dtype && h->raw_order == order &&
+        h->raw_copy.size() == bytes && memcmp(h->raw_copy.data(), planes, bytes) == 0)
+        return GPP_OK;
     DeviceGuard guard(h->device);
+    // the Keras feed casts to float32 (run_network.py:105); row-major N x 4
+    std::vector<float> rows(4 * (size_t)n_planes);
+    for (size_t j = 0; j < (size_t)n_planes; ++j)
+        for (int c = 0; c < 4; ++c) {
+            const size_t src = order ? (size_t)c * n_planes + j : 4 * j + c;
+            rows[4 * j + c] = dtype ? (float)static_cast<const double *>(planes)[src] : static_cast<const float *>(planes)[src];
+        }
     // all earlier work of this handle that may still read the old database must be done
     GPP_CUDA(cudaDeviceSynchronize());
     int rc = ensure_plane_capacity(h, n_planes);
     if (rc) return rc;
     cudaStream_t s = h->streams[0];
-    GPP_CUDA(cudaMemcpyAsync(h->d_raw, planes, bytes, cudaMemcpyHostToDevice, s));
+    GPP_CUDA(cudaMemcpyAsync(h->d_raw, rows.data(), sizeof(float) * rows.size(), cudaMemcpyHostToDevice, s));
     rc = normalise_on(h, n_planes, s);
     if (rc) return rc;
     GPP_CUDA(cudaStreamSynchronize(s));
     h->n_planes = n_planes;
-    h->planes_hash = hash;
-    h->planes_hash_valid = true;
+    h->raw_copy.assign(static_cast<const unsigned char *>(planes), static_cast<const unsigned char *>(planes) + bytes);
+    h->raw_dtype = dtype;
+    h->raw_order = order;
+    h->raw_valid = true;
     return GPP_OK;
+}
+
+int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes) {
+    return gpp_set_planes_raw(h, planes, n_planes, 0, 0);
 }
 
 int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, void *stream) {
     if (!h || !d_planes || n_planes <= 0) return set_error(GPP_EINVAL, "gpp_set_planes_device: bad argument");
     DeviceGuard guard(h->device);
-    if (n_planes > h->cap_planes) GPP_CUDA(cudaDeviceSynchronize());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_planes > h->cap_planes) {
+        GPP_CUDA(cudaDeviceSynchronize());
+    } else {
+        int rc = wait_for_fits(h, s);          // fits in flight on other streams still read the buffers overwritten below
+        if (rc) return rc;
+    }
     int rc = ensure_plane_capacity(h, n_planes);
     if (rc) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     GPP_CUDA(cudaMemcpyAsync(h->d_raw, d_planes, sizeof(float) * 4 * (size_t)n_planes, cudaMemcpyDeviceToDevice, s));
     rc = normalise_on(h, n_planes, s);
     if (rc) return rc;
     h->n_planes = n_planes;
-    h->planes_hash_valid = false;
+    h->raw_valid = false;
+    // later fits on other streams must see the new database
+    if (!h->planes_ready) GPP_CUDA(cudaEventCreateWithFlags(&h->planes_ready, cudaEventDisableTiming));
+    GPP_CUDA(cudaEventRecord(h->planes_ready, s));
+    h->planes_stream = s;
+    h->planes_pending = true;
     return GPP_OK;
 }
 
@@ -295,6 +312,7 @@ int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, c
     a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
     a.best = reinterpret_cast<long long *>(best_index);
     a.det_list = nullptr; a.det_count = nullptr;
+    if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
     GPP_CUDA(cudaEventRecord(h->ev_start, s));
     rc = gpp::launch_poll_f32(h, a, mode, s);
     if (rc) return rc;
@@ -319,6 +337,7 @@ int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimension
     a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
     a.best = reinterpret_cast<long long *>(best_index);
     a.det_list = nullptr; a.det_count = nullptr;
+    if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
     GPP_CUDA(cudaEventRecord(h->ev_start, s));
     rc = gpp::launch_poll_f64(h, a, s);
     if (rc) return rc;
@@ -335,32 +354,18 @@ int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimension
 // copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (fully asynchronous when
 // the caller's buffers are pinned).
 // ---------------------------------------------------------------------------------------------------
-int gpp::Staging::reserve(long long n_det, int n_img, bool f64) {
-    const size_t esz = f64 ? sizeof(double) : sizeof(float);
-    if (n_det <= cap_det && n_img <= cap_img && esz <= out_elem) return GPP_OK;
+int gpp::Staging::reserve(size_t bytes) {
+    if (bytes <= cap) return GPP_OK;
     release();
-    GPP_CUDA(cudaMalloc(&boxes, sizeof(float) * 12 * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&dims, sizeof(float) * 3 * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&orient, sizeof(int32_t) * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&pinv, sizeof(float) * 12 * (size_t)n_img));
-    GPP_CUDA(cudaMalloc(&keypoints, esz * 12 * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&keyplanes, esz * 4 * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&residuals, esz * (size_t)n_det));
-    GPP_CUDA(cudaMalloc(&best, sizeof(long long) * (size_t)n_det));
-    cap_det = n_det;
-    cap_img = n_img;
-    out_elem = esz;
+    GPP_CUDA(cudaMalloc(reinterpret_cast<void **>(&base), bytes));
+    cap = bytes;
     return GPP_OK;
 }
 
 void gpp::Staging::release() {
-    cudaFree(boxes); cudaFree(dims); cudaFree(orient); cudaFree(pinv);
-    cudaFree(keypoints); cudaFree(keyplanes); cudaFree(residuals); cudaFree(best);
-    boxes = dims = pinv = nullptr;
-    orient = nullptr;
-    keypoints = keyplanes = residuals = nullptr;
-    best = nullptr;
-    cap_det = 0; cap_img = 0; out_elem = 0;
+    cudaFree(base);
+    base = nullptr;
+    cap = 0;
 }
 
 int gpp::HostStaging::reserve(size_t bytes) {
@@ -389,14 +394,33 @@ static bool is_pageable(const void *p) {
     return attr.type == cudaMemoryTypeUnregistered;
 }
 
+// One chunk of a host call occupies one block: inputs first, outputs behind them, every array 256-byte aligned.  The
+// device staging block and the pinned host staging block use the same layout, so that a staged chunk moves with ONE
+// copy in each direction.
+struct ChunkLayout {
+    size_t o_boxes, o_dims, o_orient, o_pinv, in_end, o_kp, o_kpl, o_res, o_best, o_end;
+    ChunkLayout(size_t n_det, size_t n_img, size_t esz) {
+        auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+        o_boxes = 0;
+        o_dims = o_boxes + up(48 * n_det);
+        o_orient = o_dims + up(12 * n_det);
+        o_pinv = o_orient + up(4 * n_det);
+        in_end = o_pinv + up(48 * n_img);
+        o_kp = in_end;
+        o_kpl = o_kp + up(esz * 12 * n_det);
+        o_res = o_kpl + up(esz * 4 * n_det);
+        o_best = o_res + up(esz * n_det);
+        o_end = o_best + up(8 * n_det);
+    }
+};
+
 template <class T>
 static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, const int32_t *orient,
                          const float *pinv, int B, int D, T *keypoints, T *keyplanes, T *residuals,
                          int64_t *best, int mode) {
-    const bool f64 = sizeof(T) == 8;
     if ((long long)B * D == 0) return GPP_OK;
     DeviceGuard guard(h->device);
-    // chunk size: enough hypotheses to fill the machine a few times over, at most kMaxChunkDet detections
+    // chunk size: enough hypotheses to fill the machine a few times over, at most 65,536 detections
     const long long max_chunk_det = 65536;
     int imgs_per_chunk = (int)(max_chunk_det / (D > 0 ? D : 1));
     if (imgs_per_chunk < 1) imgs_per_chunk = 1;
@@ -407,8 +431,9 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
     while (start.back() < B) start.push_back(start.back() + imgs_per_chunk < B ? start.back() + imgs_per_chunk : B);
     const int n_chunks = (int)start.size() - 1;
     const int n_streams = n_chunks > 1 ? gpp_handle::kStreams : 1;
+    const ChunkLayout L((size_t)imgs_per_chunk * D, (size_t)imgs_per_chunk, sizeof(T));
     for (int i = 0; i < n_streams; ++i) {
-        int rc = h->stage[i].reserve((long long)imgs_per_chunk * D, imgs_per_chunk, f64);
+        int rc = h->stage[i].reserve(L.o_end);
         if (rc) return rc;
     }
     while ((int)h->chunk_events.size() < n_chunks) {
@@ -417,37 +442,35 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         GPP_CUDA(cudaEventCreate(&b));
         h->chunk_events.push_back(std::make_pair(a, b));
     }
-    // Pageable caller memory and more than one chunk: go through the pinned staging blocks (see HostStaging)
-    const bool staged = n_chunks > 1 && (is_pageable(boxes) || is_pageable(dims) || is_pageable(orient) ||
-                                         is_pageable(pinv) || is_pageable(keypoints) || is_pageable(keyplanes) ||
-                                         is_pageable(residuals) || (best && is_pageable(best)));
-    const size_t cd = (size_t)imgs_per_chunk * D, ci = (size_t)imgs_per_chunk;
-    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_boxes = 0, o_dims = o_boxes + up(48 * cd), o_orient = o_dims + up(12 * cd),
-                 o_pinv = o_orient + up(4 * cd), o_kp = o_pinv + up(48 * ci), o_kpl = o_kp + up(sizeof(T) * 12 * cd),
-                 o_res = o_kpl + up(sizeof(T) * 4 * cd), o_best = o_res + up(sizeof(T) * cd),
-                 o_end = o_best + up(8 * cd);
+    // Staged chunks go through the pinned blocks owned by the handle: pageable caller memory (an asynchronous copy from
+    // or to pageable memory blocks the host until it is done, which would serialise the chunks), and every small call
+    // (a single image is 6.4 KB in and 7.6 KB out: one copy each way instead of four).
+    const bool small = n_chunks == 1 && (long long)B * D <= 16384;
+    const bool staged = small || is_pageable(boxes) || is_pageable(dims) || is_pageable(orient) || is_pageable(pinv) ||
+                        is_pageable(keypoints) || is_pageable(keyplanes) || is_pageable(residuals) ||
+                        (best && is_pageable(best));
     if (staged)
         for (int i = 0; i < n_streams; ++i) {
-            int rc = h->hstage[i].reserve(o_end);
+            int rc = h->hstage[i].reserve(L.o_end);
             if (rc) return rc;
         }
+    const size_t out_end = best ? L.o_end : L.o_best;
     // copies the finished outputs of chunk c from its pinned block to the caller's arrays
     auto drain = [&](int c) -> int {
         const int b0 = start[c], nb = start[c + 1] - start[c];
         const size_t m0 = (size_t)b0 * D, nm = (size_t)nb * D;
         gpp::HostStaging &hs = h->hstage[c % n_streams];
         GPP_CUDA(cudaEventSynchronize(hs.done));
-        memcpy(keypoints + 12 * m0, hs.base + o_kp, sizeof(T) * 12 * nm);
-        memcpy(keyplanes + 4 * m0, hs.base + o_kpl, sizeof(T) * 4 * nm);
-        memcpy(residuals + m0, hs.base + o_res, sizeof(T) * nm);
-        if (best) memcpy(best + m0, hs.base + o_best, sizeof(long long) * nm);
+        memcpy(keypoints + 12 * m0, hs.base + L.o_kp, sizeof(T) * 12 * nm);
+        memcpy(keyplanes + 4 * m0, hs.base + L.o_kpl, sizeof(T) * 4 * nm);
+        memcpy(residuals + m0, hs.base + L.o_res, sizeof(T) * nm);
+        if (best) memcpy(best + m0, hs.base + L.o_best, sizeof(long long) * nm);
         return GPP_OK;
     };
     for (int c = 0; c < n_chunks; ++c) {
         const int b0 = start[c], nb = start[c + 1] - start[c];
         const long long m0 = (long long)b0 * D, nm = (long long)nb * D;
-        gpp::Staging &st = h->stage[c % n_streams];
+        unsigned char *dev = h->stage[c % n_streams].base;
         gpp::HostStaging &hs = h->hstage[c % n_streams];
         cudaStream_t s = h->streams[c % n_streams];
         const float *src_boxes = boxes + 12 * m0, *src_dims = dims + 3 * m0, *src_pinv = pinv + 12 * (size_t)b0;
@@ -457,43 +480,44 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
                 int rc = drain(c - n_streams);
                 if (rc) return rc;
             }
-            memcpy(hs.base + o_boxes, src_boxes, sizeof(float) * 12 * nm);
-            memcpy(hs.base + o_dims, src_dims, sizeof(float) * 3 * nm);
-            memcpy(hs.base + o_orient, src_orient, sizeof(int32_t) * nm);
-            memcpy(hs.base + o_pinv, src_pinv, sizeof(float) * 12 * nb);
-            src_boxes = reinterpret_cast<const float *>(hs.base + o_boxes);
-            src_dims = reinterpret_cast<const float *>(hs.base + o_dims);
-            src_orient = reinterpret_cast<const int32_t *>(hs.base + o_orient);
-            src_pinv = reinterpret_cast<const float *>(hs.base + o_pinv);
+            memcpy(hs.base + L.o_boxes, src_boxes, sizeof(float) * 12 * nm);
+            memcpy(hs.base + L.o_dims, src_dims, sizeof(float) * 3 * nm);
+            memcpy(hs.base + L.o_orient, src_orient, sizeof(int32_t) * nm);
+            memcpy(hs.base + L.o_pinv, src_pinv, sizeof(float) * 12 * nb);
+            GPP_CUDA(cudaMemcpyAsync(dev, hs.base, L.in_end, cudaMemcpyHostToDevice, s));
+        } else {
+            GPP_CUDA(cudaMemcpyAsync(dev + L.o_boxes, src_boxes, sizeof(float) * 12 * nm, cudaMemcpyHostToDevice, s));
+            GPP_CUDA(cudaMemcpyAsync(dev + L.o_dims, src_dims, sizeof(float) * 3 * nm, cudaMemcpyHostToDevice, s));
+            GPP_CUDA(cudaMemcpyAsync(dev + L.o_orient, src_orient, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
+            GPP_CUDA(cudaMemcpyAsync(dev + L.o_pinv, src_pinv, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
         }
-        GPP_CUDA(cudaMemcpyAsync(st.boxes, src_boxes, sizeof(float) * 12 * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.dims, src_dims, sizeof(float) * 3 * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.orient, src_orient, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
-        GPP_CUDA(cudaMemcpyAsync(st.pinv, src_pinv, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
         gpp::PollArgs<T> a;
-        a.boxes = st.boxes; a.dims = st.dims; a.orient = st.orient; a.pinv = st.pinv;
-        a.planes = f64 ? (const void *)h->d_planes64 : (const void *)h->d_planes32;
+        a.boxes = reinterpret_cast<const float *>(dev + L.o_boxes);
+        a.dims = reinterpret_cast<const float *>(dev + L.o_dims);
+        a.orient = reinterpret_cast<const int32_t *>(dev + L.o_orient);
+        a.pinv = reinterpret_cast<const float *>(dev + L.o_pinv);
+        a.planes = sizeof(T) == 8 ? (const void *)h->d_planes64 : (const void *)h->d_planes32;
         a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = nm;
-        a.keypoints = static_cast<T *>(st.keypoints);
-        a.keyplanes = static_cast<T *>(st.keyplanes);
-        a.residuals = static_cast<T *>(st.residuals);
-        a.best = best ? st.best : nullptr;
+        a.keypoints = reinterpret_cast<T *>(dev + L.o_kp);
+        a.keyplanes = reinterpret_cast<T *>(dev + L.o_kpl);
+        a.residuals = reinterpret_cast<T *>(dev + L.o_res);
+        a.best = best ? reinterpret_cast<long long *>(dev + L.o_best) : nullptr;
         a.det_list = nullptr; a.det_count = nullptr;
+        if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].first, s));
         int rc = gpp::launch_poll(h, a, mode, s);
         if (rc) return rc;
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].second, s));
-        T *dst_kp = staged ? reinterpret_cast<T *>(hs.base + o_kp) : keypoints + 12 * m0;
-        T *dst_kpl = staged ? reinterpret_cast<T *>(hs.base + o_kpl) : keyplanes + 4 * m0;
-        T *dst_res = staged ? reinterpret_cast<T *>(hs.base + o_res) : residuals + m0;
-        GPP_CUDA(cudaMemcpyAsync(dst_kp, st.keypoints, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
-        GPP_CUDA(cudaMemcpyAsync(dst_kpl, st.keyplanes, sizeof(T) * 4 * nm, cudaMemcpyDeviceToHost, s));
-        GPP_CUDA(cudaMemcpyAsync(dst_res, st.residuals, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
-        if (best) {
-            int64_t *dst_best = staged ? reinterpret_cast<int64_t *>(hs.base + o_best) : best + m0;
-            GPP_CUDA(cudaMemcpyAsync(dst_best, st.best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
+        if (staged) {
+            GPP_CUDA(cudaMemcpyAsync(hs.base + L.o_kp, dev + L.o_kp, out_end - L.o_kp, cudaMemcpyDeviceToHost, s));
+            GPP_CUDA(cudaEventRecord(hs.done, s));
+        } else {
+            GPP_CUDA(cudaMemcpyAsync(keypoints + 12 * m0, dev + L.o_kp, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
+            GPP_CUDA(cudaMemcpyAsync(keyplanes + 4 * m0, dev + L.o_kpl, sizeof(T) * 4 * nm, cudaMemcpyDeviceToHost, s));
+            GPP_CUDA(cudaMemcpyAsync(residuals + m0, dev + L.o_res, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
+            if (best)
+                GPP_CUDA(cudaMemcpyAsync(best + m0, dev + L.o_best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
         }
-        if (staged) GPP_CUDA(cudaEventRecord(hs.done, s));
     }
     if (staged)
         for (int c = (n_chunks > n_streams ? n_chunks - n_streams : 0); c < n_chunks; ++c) {

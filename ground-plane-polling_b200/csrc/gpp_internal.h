@@ -13,16 +13,11 @@ namespace gpp {
 
 int set_error(int code, const char *fmt, ...);
 
-// device-side staging buffers of one stream of the host entry point
+// device-side staging block of one stream of the host entry point (one chunk: inputs, then outputs; see ChunkLayout)
 struct Staging {
-    float *boxes = nullptr, *dims = nullptr, *pinv = nullptr;
-    int32_t *orient = nullptr;
-    void *keypoints = nullptr, *keyplanes = nullptr, *residuals = nullptr;
-    long long *best = nullptr;
-    long long cap_det = 0;
-    int cap_img = 0;
-    size_t out_elem = 0;
-    int reserve(long long n_det, int n_img, bool f64);
+    unsigned char *base = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
     void release();
 };
 
@@ -89,8 +84,14 @@ struct gpp_handle {
     unsigned long long *d_pairs = nullptr;   // pair-interleaved fp32 copy, padded to 64 planes (gpp_poll2.cuh)
     int n_pairs_padded = 0;
     int n_planes = 0, cap_planes = 0;
-    uint64_t planes_hash = 0;
-    bool planes_hash_valid = false;
+    // bytes of the last host upload as the caller passed them (gpp_set_planes_raw compares before doing any work)
+    std::vector<unsigned char> raw_copy;
+    int raw_dtype = 0, raw_order = 0;
+    bool raw_valid = false;
+    // a device-side database update (gpp_set_planes_device) that fits on other streams have to wait for
+    cudaEvent_t planes_ready = nullptr;
+    cudaStream_t planes_stream = nullptr;
+    bool planes_pending = false;
     // host-entry plumbing
     cudaStream_t streams[kStreams] = {nullptr, nullptr};
     gpp::Staging stage[kStreams];

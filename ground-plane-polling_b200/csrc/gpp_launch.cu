@@ -154,8 +154,10 @@ constexpr size_t kSmem1 = sizeof(float4) * kStages * kTile32 + 2 * kStages * siz
                           2 * kWarps * sizeof(WarpPartial<float>);
 
 // Resident-database kernel (gpp_poll3.cuh): one persistent CTA of kWarps3 warps per SM
+// 32 warps at 64 registers (no spills once the rarely used detection constants are parked in shared memory): measured
+// 4.84e11 hypotheses/s (VERIFIED, C4) against 4.77e11 with 28 warps / 72 registers and 4.49e11 with 24 / 80
 #ifndef GPP_WARPS3
-#define GPP_WARPS3 24
+#define GPP_WARPS3 32
 #endif
 constexpr int kWarps3 = GPP_WARPS3;
 typedef void (*Poll3Fn)(const PollArgs3);
@@ -229,6 +231,7 @@ static int launch_poll3(gpp_handle *h, const PollArgs<float> &a, int mode, cudaS
     int n_seg = 1;
     if (h->force_seg > 0) n_seg = h->force_seg;
     else if (a.n_det < 3 * slots) n_seg = (int)((3 * slots + a.n_det - 1) / a.n_det);
+    if (n_seg > 16 && h->force_seg <= 0) n_seg = 16;        // measured: a single image is fastest with 16 segments
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;
     if (a.n_det > h->seg_det_cap || a.n_det * n_seg > h->seg_items_cap) n_seg = 1;
@@ -244,6 +247,19 @@ static int launch_poll3(gpp_handle *h, const PollArgs<float> &a, int mode, cudaS
     if (grid > n_items) grid = n_items;
     const size_t smem = smem3_bytes(kWarps3, res);
     poll3_variant(mode == GPP_MODE_VERIFIED, b.n_seg > 1)<<<(unsigned)grid, kWarps3 * 32, smem, s>>>(b);
+#ifdef GPP_STATS
+    if (mode == GPP_MODE_VERIFIED) {
+        unsigned long long st[8], zero[8] = {0};
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(st, g_stats3, sizeof(st));
+        cudaMemcpyToSymbol(g_stats3, zero, sizeof(zero));
+        const double rows = double(st[0] + st[2]), items = double(st[5] ? st[5] : 1);
+        fprintf(stderr, "[gpp stats3] items %llu (identical-rays %llu) seg %d resident %d: rows/item %.1f, all-six %.1f%% (past stage 1: %.1f%% "
+                "of them), general %.1f%%, rows with survivors %.2f%%; exact verifications/item %.1f, flushes/item %.2f\n",
+                st[5], st[6], b.n_seg, res, rows / items, 100.0 * st[0] / (rows ? rows : 1), 100.0 * st[1] / (st[0] ? st[0] : 1),
+                100.0 * st[2] / (rows ? rows : 1), 100.0 * st[7] / (rows ? rows : 1), double(st[3]) / items, double(st[4]) / items);
+    }
+#endif
     h->launches += 1;
     w.used = true;
     e = cudaEventRecord(w.done, s);

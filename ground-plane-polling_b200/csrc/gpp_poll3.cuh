@@ -57,6 +57,25 @@ __device__ __forceinline__ Detection<ExactF32> load_det_exact(const float *detx)
     return det;
 }
 
+// The detection constants that only the rare paths of the VERIFIED filter read (stage 2 of the all-six phase, the general
+// phase, the threshold updates) are parked in the warp's shared-memory slot and fetched where those paths begin, so that
+// the hot first stage keeps ten constants in registers instead of nineteen.
+constexpr int kColdOffset = 20;      // floats; the exact constants occupy [0, 18)
+__device__ __forceinline__ void store_cold(float *detx, const DetConst &D) {
+    float *c = detx + kColdOffset;
+    c[0] = D.ft[0]; c[1] = D.ft[1]; c[2] = D.T; c[3] = D.G;
+    c[4] = D.msT; c[5] = D.mc; c[6] = D.td[0]; c[7] = D.td[4];
+    c[8] = D.td[5];
+}
+__device__ __forceinline__ void load_cold(DetConst &D, const float *detx) {
+    const uint32_t a = smem_u32(detx + kColdOffset);
+    float x8, pad0, pad1, pad2;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(D.ft[0]), "=f"(D.ft[1]), "=f"(D.T), "=f"(D.G) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(D.msT), "=f"(D.mc), "=f"(D.td[0]), "=f"(D.td[4]) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(x8), "=f"(pad0), "=f"(pad1), "=f"(pad2) : "r"(a));
+    D.td[5] = x8;
+}
+
 // (max-votes, best residual) as one 64-bit key that grows when the pair improves: more votes first, then a smaller
 // residual (r >= +0, never NaN: the bit pattern orders like the value)
 __device__ __forceinline__ unsigned long long seg_key(int M, float r) {
@@ -107,7 +126,20 @@ struct RowSource {
 // The body of the row function is the filter of poll2_kernel<..., kVMode = 1> (see the comments there and DESIGN.md
 // section 4.1): all-six phase in two stages, general phase with the order-statistic pre-test, early bounds from
 // certain planes, survivors queued and re-evaluated 32 at a time in the exact arithmetic.
+// development counters (-DGPP_STATS, printed by launch_poll3): [0] rows in the all-six phase, [1] of them past stage 1,
+// [2] rows in the general phase, [3] exact verifications, [4] flushes, [5] work items, [6] items polled in the
+// identical-rays form, [7] rows past the whole filter (something queued)
+#ifdef GPP_STATS
+__device__ unsigned long long g_stats3[8];
+#define GPP_STAT3(i, n) (stat[i] += (n))
+#else
+#define GPP_STAT3(i, n) ((void)0)
+#endif
+
 struct VerifiedScan {
+#ifdef GPP_STATS
+    unsigned int stat[8];
+#endif
     LaneState<float> st;   // exact selection state of this lane (max-votes, best residual, index)
     float wbest;           // warp-uniform: best EXACT residual so far at max-votes Mcur (or an early upper bound of it)
     float wthr;            // (wbest + mc)(1 + 2^-18)
@@ -120,10 +152,16 @@ struct VerifiedScan {
         wthr = __int_as_float(0x7f800000);
         qn = 0;
         Mcur = -1;
+#ifdef GPP_STATS
+        for (int i = 0; i < 8; ++i) stat[i] = 0;
+        stat[5] = 1;
+#endif
     }
 
     // adopt a bound found by another segment of the same detection (exact values, published through seg_best)
-    __device__ __forceinline__ void adopt(unsigned long long key, const DetConst &D) {
+    __device__ __forceinline__ void adopt(unsigned long long key, const float *detx) {
+        DetConst D;
+        load_cold(D, detx);
         const int M = int(unsigned(key >> 32)) - 1;
         const float r = __uint_as_float(0xffffffffu - unsigned(key & 0xffffffffu));
         if (M > Mcur) {
@@ -139,6 +177,8 @@ struct VerifiedScan {
     __device__ __forceinline__ void flush(const float *detx, const float4 *__restrict__ planes, const int *queue,
                                           int lane, bool all, const DetConst &D) {
         const Detection<ExactF32> det = load_det_exact(detx);
+        GPP_STAT3(4, 1);
+        GPP_STAT3(3, all ? qn : (qn & ~31));
         while (qn >= 32) {
             qn -= 32;
             verify_general(det, planes, queue[qn + lane], st);
@@ -159,10 +199,12 @@ struct VerifiedScan {
         wthr = (wbest + D.mc) * 1.0000038f;
     }
 
-    // One row: c0 / c1 hold this lane's pair of row r on entry and of row r + 1 (if `more`) on return.
-    __device__ __forceinline__ void row(const DetConst &D, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+    // One row: c0 / c1 hold this lane's pair of the current row on entry and of the next row (if any) on return.
+    // `Dh` carries the hot constants only (rays l, m, r, the bottom-face targets, the margin scale).
+    __device__ __forceinline__ void row(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
                                         const int N, const int lane, int *queue, const float *detx,
                                         const float4 *__restrict__ planes) {
+        DetConst D = Dh;
         PairResult h;
         bool trig0, trig1, urgent = false;
         Bottom g;
@@ -170,6 +212,7 @@ struct VerifiedScan {
         if (src.more()) src.load_next(c0, c1);
         if (Mcur == 6) {
             // stage 1: the bottom face only
+            GPP_STAT3(0, 1);
             eval_bottom_rest<true, true>(D, g);
             h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
             h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
@@ -180,6 +223,8 @@ struct VerifiedScan {
                 if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) return;
             }
             // stage 2: X_t, the height and the two slanted edges, the full margin
+            GPP_STAT3(1, 1);
+            load_cold(D, detx);
             ulonglong2 v0, v1;
             src.load_again(v0, v1);
             const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
@@ -219,6 +264,8 @@ struct VerifiedScan {
             trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
             trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
         } else {
+            GPP_STAT3(2, 1);
+            load_cold(D, detx);
             eval_bottom_rest<false, true>(D, g);
             {
                 ulonglong2 v0, v1;
@@ -271,6 +318,7 @@ struct VerifiedScan {
         const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
         const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
         if (b0 | b1) {
+            GPP_STAT3(7, 1);
             const unsigned below = (1u << lane) - 1u;
             if (q0) queue[qn + __popc(b0 & below)] = j;
             qn += __popc(b0);
@@ -287,10 +335,15 @@ struct VerifiedScan {
                                            int lane) {
         if (qn > 0) {
             const Detection<ExactF32> det = load_det_exact(detx);
+            GPP_STAT3(3, qn);
             if (lane < qn) verify_general(det, planes, queue[lane], st);
             qn = 0;
             __syncwarp();
         }
+#ifdef GPP_STATS
+        if (lane == 0)
+            for (int i = 0; i < 8; ++i) atomicAdd(&g_stats3[i], (unsigned long long)stat[i]);
+#endif
     }
     __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx) const {
         Mw = __reduce_max_sync(0xffffffffu, st.M);
@@ -399,7 +452,7 @@ __device__ __forceinline__ bool same_detection(const PollArgs3 &a, long long m, 
     return __all_sync(0xffffffffu, x == y);
 }
 
-constexpr int kWarpSmem3 = kVerifyQueue * (int)sizeof(int) + 20 * (int)sizeof(float);   // queue + exact constants
+constexpr int kWarpSmem3 = kVerifyQueue * (int)sizeof(int) + 32 * (int)sizeof(float);   // queue + exact / cold constants
 __host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
     return size_t(resident_rows) * 1024 + size_t(warps) * kWarpSmem3 + 16;
 }
@@ -453,6 +506,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
 
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
         DetConst D;
+        bool same_rays;
         {
             Detection<ExactF32> det0;
             load_detection<ExactF32, ExactF32>(det0, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
@@ -460,6 +514,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
 #pragma unroll
             for (int i = 0; i < 6; ++i) D.td[i] = det0.td[i];
             fast_constants(D, det0);
+            same_rays = kVerified && same_ground_rays(det0);
             __syncwarp();                            // the previous item's readers are done
             if (lane == 0) {
 #pragma unroll
@@ -468,6 +523,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) detx[12 + i] = det0.td[i];
+                store_cold(detx, D);
             }
             __syncwarp();
         }
@@ -480,7 +536,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
         src.load_again(c0, c1);
         int Mw, idx;
         float rbest;
-        if (kVerified) {
+        if (kVerified && same_rays) {
+            // FilterDetections' padding row: all its hypotheses are within rounding noise of each other, so the filter
+            // cannot drop any -- every plane of the segment in the exact arithmetic right away, in the cheap form that
+            // identical rays allow (gpp_math.cuh)
+            const Detection<ExactF32> det = load_det_exact(detx);
+            LaneState<float> st;
+            st.reset(FLT_MAX);
+            const int p_end = min(N, r_end << 6);
+#pragma unroll 2
+            for (int j = (r_begin << 6) + lane; j < p_end; j += 32) {
+                const float4 pl = __ldg(args.planes + j);
+                float X[4][3];
+                int V; float R; bool z;
+                hypothesis_same_rays<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
+                st.update(V, R, z, j, FLT_MAX);
+            }
+            Mw = __reduce_max_sync(0xffffffffu, st.M);
+            rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
+            idx = st.bestIdx;
+#ifdef GPP_STATS
+            if (lane == 0) { atomicAdd(&g_stats3[5], 1ull); atomicAdd(&g_stats3[6], 1ull); }
+#endif
+        } else if (kVerified) {
             VerifiedScan sc;
             sc.begin();
             for (; src.rows_left > 0; src.advance()) {
@@ -493,7 +571,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
                 if (kSeg && (sc.Mcur != Mb || sc.wbest < wb) && lane == 0)
                     atomicMax(args.seg_best + m, seg_key(sc.Mcur, sc.wbest));
-                if (share) sc.adopt(key, D);
+                if (share) sc.adopt(key, detx);
             }
             sc.finish(detx, args.planes, queue, lane);
             sc.result(Mw, rbest, idx);
@@ -595,15 +673,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             word = (lane == 14) ? pl.z : word;
             word = (lane == 15) ? pl.w : word;
             word = (lane == 16) ? rr : word;
-            // this row and the identical rows that follow it in the image
-            long long n = m;
-            do {
+            // this row and the identical rows that follow it in the image (their claims were skipped).  The length of
+            // the run is found 32 rows at a time -- lane i compares row m + 1 + i with its predecessor -- so that a
+            // padded image costs a few load latencies, not one per padding row.
+            const long long image_end = (m / args.dets_per_image + 1) * (long long)args.dets_per_image;
+            long long run_end = m + 1;
+            for (long long base = m + 1; base < image_end; base += 32) {
+                const long long n = base + lane;
+                bool same = n < image_end;
+                if (same) {
+                    const unsigned *bx = reinterpret_cast<const unsigned *>(args.boxes) + 12 * n;
+                    const unsigned *dm = reinterpret_cast<const unsigned *>(args.dims) + 3 * n;
+                    unsigned diff = (unsigned)(__ldg(args.orient + n) ^ __ldg(args.orient + n - 1));
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) diff |= __ldg(bx + i) ^ __ldg(bx + i - 12);     // all loads in flight at once
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) diff |= __ldg(dm + i) ^ __ldg(dm + i - 3);
+                    same = diff == 0u;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, same);
+                const int lead = __ffs(~b) - 1;                   // rows of this batch that continue the run (-1: all 32)
+                run_end = base + (lead < 0 ? 32 : lead);
+                if (lead >= 0) break;
+            }
+            for (long long n = m; n < run_end; ++n) {
                 if (lane < 12) args.keypoints[12 * n + lane] = word;
                 else if (lane < 16) args.keyplanes[4 * n + (lane - 12)] = word;
                 else if (lane == 16) args.residuals[n] = word;
                 else if (lane == 17 && args.best) args.best[n] = idx;
-                ++n;
-            } while (n < args.n_det && (n % args.dets_per_image) != 0 && same_detection(args, n, m, lane));
+            }
         }
     }
 

@@ -41,7 +41,7 @@ class PlanePoller(object):
         _lib.check(self._lib.gpp_create(int(device), ctypes.byref(h)), 'gpp_create')
         self._h = h
         self.device = int(device)
-        self._dev_planes_key = None
+        self._dev_planes = None      # (tensor, version) of the last device-side database, held so that it stays alive
 
     def close(self):
         if getattr(self, '_h', None):
@@ -58,11 +58,18 @@ class PlanePoller(object):
     def set_planes(self, planes):
         """Upload a raw (N, 4) road-plane database (any float dtype / memory order, e.g. the float64
         Fortran-ordered array scipy.io.loadmat returns, run_network.py:75).  Idempotent on equal content."""
-        p = _f32(planes)
+        p = np.asarray(planes)
         if p.ndim != 2 or p.shape[1] != 4 or p.shape[0] < 1:
             raise ValueError('planes must have shape (N, 4) with N >= 1, got %r' % (p.shape,))
-        _lib.check(self._lib.gpp_set_planes(self._h, _lib.ptr(p), p.shape[0]), 'gpp_set_planes')
-        self._dev_planes_key = None
+        # the callers' array goes to the library as it is (float64 / Fortran order from loadmat included): the cast
+        # Keras applies at feed and the "same database as last time?" test (an exact byte comparison) happen there
+        if p.dtype not in (np.float32, np.float64) or not (p.flags['C_CONTIGUOUS'] or p.flags['F_CONTIGUOUS']):
+            p = _f32(p)
+        order = 0 if p.flags['C_CONTIGUOUS'] else 1
+        rc = self._lib.gpp_set_planes_raw(self._h, p.ctypes.data_as(ctypes.c_void_p), p.shape[0],
+                                          1 if p.dtype == np.float64 else 0, order)
+        _lib.check(rc, 'gpp_set_planes_raw')
+        self._dev_planes = None
 
     @property
     def num_planes(self):
@@ -133,13 +140,15 @@ class PlanePoller(object):
         p = planes.detach().to(torch.float32).contiguous()
         if p.dim() != 2 or p.shape[1] != 4 or p.shape[0] < 1:
             raise ValueError('planes must have shape (N, 4), got %r' % (tuple(p.shape),))
-        key = (planes.data_ptr(), planes._version, tuple(planes.shape), planes.dtype)
-        if key == self._dev_planes_key:
+        # Skip the upload only for the very same tensor OBJECT with an unchanged version counter.  The object is kept
+        # alive here, so neither its identity nor its storage can be recycled for other content (a data_ptr / shape
+        # key would be: the caching allocator hands a freed block to the next tensor of the same size).
+        if self._dev_planes is not None and self._dev_planes[0] is planes and self._dev_planes[1] == planes._version:
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.gpp_set_planes_device(self._h, ctypes.c_void_p(p.data_ptr()), p.shape[0],
                                                    ctypes.c_void_p(stream)), 'gpp_set_planes_device')
-        self._dev_planes_key = key
+        self._dev_planes = (planes, planes._version)
 
     def fit_torch(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False):
         """Device-resident call: CUDA tensors in, CUDA tensors out, enqueued on torch's current stream,
@@ -276,12 +285,15 @@ def _plane_groups(planes, B):
         return [(0, B, planes[0])]
     if planes.shape[0] != B:
         raise ValueError('planes batch %d does not match boxes batch %d' % (planes.shape[0], B))
-    groups, start = [], 0
-    for b in range(1, B + 1):
-        if b == B or not np.array_equal(planes[b], planes[start]):
-            groups.append((start, b, planes[start]))
-            start = b
-    return groups
+    if planes.flags['C_CONTIGUOUS'] and planes[0].nbytes > 0:
+        # every image as ONE opaque item: neighbouring images are compared with memcmp instead of element by element
+        # (a np.tile'd database for a large batch is gigabytes of compares otherwise)
+        rows = planes.reshape(B, -1).view(np.dtype((np.void, planes[0].nbytes))).ravel()
+        cuts = np.flatnonzero(rows[1:] != rows[:-1]) + 1
+    else:
+        cuts = np.array([b for b in range(1, B) if not np.array_equal(planes[b], planes[b - 1])], dtype=np.int64)
+    bounds = [0] + [int(c) for c in cuts] + [B]
+    return [(bounds[i], bounds[i + 1], planes[bounds[i]]) for i in range(len(bounds) - 1)]
 
 
 def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False, device=None,
@@ -348,9 +360,11 @@ def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=N
     poller = get_poller(boxes.device.index if boxes.device.index is not None else torch.cuda.current_device())
     if isinstance(planes, torch.Tensor):
         if planes.dim() == 3:
-            if planes.shape[0] != 1 and not bool((planes == planes[:1]).all()):
-                raise ValueError('fit_road_planes_torch takes one database per call; use fit_road_planes '
-                                 '(numpy) for per-image databases')
+            # one database per call: (1, N, 4), or a broadcast view of one (expand(): stride 0 along the batch).  A
+            # materialised (B, N, 4) tensor would need a device-wide compare and a host sync to accept, so it is not.
+            if planes.shape[0] != 1 and planes.stride(0) != 0:
+                raise ValueError('fit_road_planes_torch takes one database per call: pass (N, 4), (1, N, 4) or an '
+                                 'expand()ed view; use fit_road_planes (numpy) for per-image databases')
             planes = planes[0]
         poller.set_planes_torch(planes)
     else:

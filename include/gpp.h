@@ -64,12 +64,19 @@ int gpp_destroy(gpp_handle *h);
 /* Upload one road-plane database: `planes` is host memory, N x 4 floats [a, b, c, d] per row, RAW (as
  * loaded from road_planes_database_*.mat, run_network.py:75, cast to float32 like the Keras feed does).
  * The sign flip and unit-normal normalisation of fit_road_planes.py:75-77 run once on the device.
- * Re-sending identical content is detected (64-bit content hash) and costs no upload, because every
- * reference caller re-feeds the same database with every image (run_network.py:105,
+ * Re-sending identical content is detected (byte comparison with the last upload) and costs no upload, because
+ * every reference caller re-feeds the same database with every image (run_network.py:105,
  * preprocessing/kitti.py:220).  Replaces the `planes` input tensor of FitRoadPlanes.call
  * (fit_road_planes.py:152-163, models/retinanet.py:396). */
 int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes);
-/* Same, from a device pointer (stream-ordered on `stream`, no hash shortcut). */
+/* Same for the array exactly as the reference's callers hold it: `dtype` 0 = float32, 1 = float64 (what
+ * scipy.io.loadmat returns, run_network.py:75); `order` 0 = row-major N x 4, 1 = column-major (Fortran order, again
+ * what loadmat returns).  The cast to float32 is the one Keras applies at feed.  The library keeps a byte copy of the
+ * last upload and compares before doing anything else, so that re-sending the same database with every image
+ * (run_network.py:105) costs one memcmp. */
+int gpp_set_planes_raw(gpp_handle *h, const void *planes, int n_planes, int dtype, int order);
+/* Same, from a device pointer (stream-ordered on `stream`, no shortcut; fits of this handle still in flight on other
+ * streams are waited for, and later fits on other streams wait for the update). */
 int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, void *stream);
 int gpp_num_planes(const gpp_handle *h);
 /* Copy the normalised database (N x 4 floats) back to host -- the table `keyplanes` rows are taken from. */

@@ -33,7 +33,8 @@ def main():
     out = {'lib': os.path.basename(gpp_b200._lib.LIB_PATH)}
     quick = '--quick' in sys.argv
     cases = [('C4_4096x100x22k', 4096, '22k'), ('C3_64x100x10k', 64, '10k'), ('1x100x22k', 1, '22k'),
-             ('C2_1x100x1k', 1, '1k'), ('16x100x22k', 16, '22k'), ('512x100x22k', 512, '22k')]
+             ('C2_1x100x1k', 1, '1k'), ('16x100x22k', 16, '22k'), ('512x100x22k', 512, '22k'), ('1024x100x10k', 1024, '10k'),
+             ('1024x100x1k', 1024, '1k')]
     for name, B, tag in cases:
         pl = planes_of(tag)
         pool = min(B, 256)

@@ -119,3 +119,26 @@ def test_runtime_audit_counts(gpp, poller):
     _same(again, want[:3])
     gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified')                  # audit off again
     assert poller.audit_counts() == (c1, b1)
+
+
+def test_identical_rays_take_the_cheap_exact_form_bit_for_bit(gpp, poller):
+    """Rows whose l / m / r rays are bitwise identical (FilterDetections' -1 padding; here also whole images, through a
+    P_inv that maps every pixel to one ray) are polled in the exact arithmetic directly, in a form that computes the one
+    point on the plane once.  The database holds planes parallel to that ray (point at infinity -> NaN differences: the
+    general form must take over) and a b = 0 plane (NaN after normalisation)."""
+    base = load_planes('1k')[:300].astype(np.float32)
+    odd = np.array([[0.3, -0.5, 0.25, 1.3], [-0.2, 0.5, -0.25, -1.1], [1.0, 0.0, 0.0, 2.0], [0.0, -1.0, 0.0, 1.65]], np.float32)
+    planes = np.concatenate([base[:100], odd, base[100:], odd[:2]], axis=0)
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 40, base, seed=515, n_valid=22)
+    P_inv = P_inv.astype(np.float32).copy()
+    P_inv[1] = np.array([[0, 0, 0], [0, 0, 0.5], [0, 0, 1], [0, 0, 0]], np.float32)      # every pixel -> ray (0, 0.5, 1)
+    P_inv[2] = np.array([[0, 0, 0.1], [0, 0, 0.5], [0, 0, -1], [0, 0, 0]], np.float32)   # sign flip of the ray (z < 0)
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    for n_seg in (0, 1, 5):
+        poller.debug_set_schedule(n_seg, -1)
+        try:
+            got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
+        finally:
+            poller.debug_set_schedule(0, -1)
+        _same(got, want)
+    _same(gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='exact', return_index=True), want)
