@@ -42,8 +42,8 @@ if ROOT not in sys.path:
 
 W_ALG = 148.0                      # algorithmic FLOP per hypothesis, SURVEY.md section 8.4
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-KERNEL_OF_MODE = {'verified': 'gpp::poll2_kernel<PackFast, verified>',
-                  'fast': 'gpp::poll2_kernel<PackFast>', 'exact': 'gpp::poll_kernel<ExactF32>'}
+KERNEL_OF_MODE = {'verified': 'gpp::poll3_kernel<32, verified>',
+                  'fast': 'gpp::poll3_kernel<32, fast>', 'exact': 'gpp::poll_kernel<ExactF32>'}
 METRIC = 'ground-plane hypotheses/sec (dets x planes)'
 UNIT = 'hypotheses/s'
 
@@ -68,14 +68,14 @@ def load_planes(tag):
 
 
 def make_workload(images, dets, planes, seed):
-    """Seeded synthetic KITTI-shaped detections.  A pool of 256 distinct images is
-    generated and tiled to `images` (generation is host-side numpy and not part of any timed region)."""
+    """Seeded synthetic KITTI-shaped detections: `images` DISTINCT images, generated on the
+    host in chunks (numpy; not part of any timed region)."""
     from gpp_b200.utils import synthetic
-    pool = min(images, 256)
-    boxes, dims, orient, P_inv = synthetic.synth_detections(pool, dets, planes, seed=seed)
-    rep = (images + pool - 1) // pool
-    tile = lambda a: np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:images])  # noqa: E731
-    return tile(boxes), tile(dims), tile(orient), tile(P_inv.astype(np.float32))
+    parts = []
+    for c0 in range(0, images, 512):
+        parts.append(synthetic.synth_detections(min(512, images - c0), dets, planes, seed=seed * 1000 + c0 // 512))
+    cat = lambda k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=0))  # noqa: E731
+    return cat(0), cat(1), cat(2), cat(3).astype(np.float32)
 
 
 class ClockSampler(object):
@@ -188,11 +188,34 @@ def run_reference(args, rank):
 
 
 def workload_config(args, planes):
-    return {'workload': 'C4: %d images x %d detections x road_planes_database_%s (%d planes) per GPU, KITTI P2 '
-                        '1242x375 scaled 1333/1242' % (args.images, args.dets, args.planes, planes.shape[0]),
+    return {'workload': 'C4: %d distinct images x %d detections x road_planes_database_%s (%d planes) per GPU, KITTI P2 '
+                        '1242x375 scaled 1333/1242, every row valid, key-point noise 1.5 px' % (
+                            args.images, args.dets, args.planes, planes.shape[0]),
             'images_per_gpu': args.images, 'detections_per_image': args.dets, 'planes': int(planes.shape[0]),
             'mode': args.mode, 'sharding': 'images sharded, plane database replicated, no collective',
             'l2': 'flushed between timed steps (256 MiB write); working set < L2'}
+
+
+def ncu_pipe_summary():
+    """FMA-pipe / issue utilisation of the headline kernel from the newest committed ncu summary (profiles/): the
+    148-FLOP roofline fraction counts algorithmic work, these say how busy the pipes really were."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_poll3_verified_c4_ncu.txt')))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        text = f.read()
+    def grab(key):
+        m = re.search(re.escape(key) + r'\s+([0-9.]+)', text)
+        return float(m.group(1)) if m else None
+    return {'source': 'profiles/' + os.path.basename(files[-1]) + ' (ncu --set full capture of this launch)',
+            'fma_pipe_active_pct': grab('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'),
+            'xu_pipe_pct': grab('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
+            'issue_active_pct': grab('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+            'warps_active_pct': grab('sm__warps_active.avg.pct_of_peak_sustained_active'),
+            'dram_bytes_per_launch': (lambda r, w: None if r is None or w is None else r * 1e6 + w * 1e3)(
+                grab('dram__bytes_read.sum'), grab('dram__bytes_write.sum'))}
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -246,8 +269,10 @@ def main():
 
     planes = load_planes(args.planes)
     N = int(planes.shape[0])
-    boxes, dims, orient, P_inv = make_workload(args.images, args.dets, planes, seed=3 + rank)
-    hyp_per_step = float(args.images) * args.dets * N
+    B, D = args.images, args.dets
+    # weak leg: every rank has its own batch (seed 3 + rank); the strong leg shards rank 0's batch (seed 3)
+    boxes, dims, orient, P_inv = make_workload(B, D, planes, seed=3 + rank)
+    hyp_per_step = float(B) * D * N
     poller = gpp_b200.get_poller(local_rank)
     poller.set_planes(planes)
 
@@ -260,10 +285,9 @@ def main():
     to, tp = torch.from_numpy(orient).to(dev), torch.from_numpy(P_inv).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def device_step():
+    def device_step(t=None):
         flush.fill_(1)                                       # evict L2 (untimed: kernel time comes from events)
-        out = poller.fit_torch(tb, td, to, tp, mode=args.mode)
-        return out
+        return poller.fit_torch(*(t or (tb, td, to, tp)), mode=args.mode, return_index=True)
 
     # nvidia-smi's start-up takes a driver lock that stalls a running kernel for tens of ms: start the sampler
     # BEFORE the warm-up steps so that only its steady 100 ms polling overlaps the timed region
@@ -279,7 +303,7 @@ def main():
     barrier()
     w0 = time.time()
     for _ in range(args.steps):
-        device_step()
+        timed_out = device_step()
         torch.cuda.synchronize()
         kernel_ms.append(poller.last_kernel_ms())            # CUDA events around the kernel, launching stream
     barrier()
@@ -289,35 +313,113 @@ def main():
     dev_ms = max_over_ranks(sum(kernel_ms))
     value = world * hyp_per_step * args.steps / (dev_ms * 1e-3)
 
-    # ---------------- end-to-end leg: public numpy API, pinned host buffers, copies inside the timed region
+    # ---------------- parity of the run that was just timed: the first 8 images against the C oracle (rank 0)
+    parity = None
+    if rank == 0:
+        from oracle import c_oracle
+        n_chk = min(8, B)
+        want = c_oracle.fit_road_planes_c(boxes[:n_chk], dims[:n_chk], orient[:n_chk], P_inv[:n_chk], planes, return_index=True)
+        got = [t[:n_chk].cpu().numpy() for t in timed_out]
+        bad = int(np.sum(got[3] != want[3]))
+        bits = all(np.array_equal(g, w, equal_nan=True) for g, w in zip(got, want))
+        parity = {'parity_checked': True, 'parity_mismatches': bad, 'outputs_bit_identical': bool(bits),
+                  'parity_rows': int(n_chk * D), 'parity_against': 'oracle/gpp_oracle.c on the last timed step'}
+
+    # ---------------- end-to-end leg: public numpy API, host buffers, copies inside the timed region
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
         t.numpy()[...] = a
         return t
-    hb, hd, ho, hp = pinned(boxes), pinned(dims), pinned(orient), pinned(P_inv)
-    B, D = args.images, args.dets
-    outs_t = [torch.empty((B, D, 4, 3), dtype=torch.float32, pin_memory=True),
-              torch.empty((B, D, 1, 4), dtype=torch.float32, pin_memory=True),
-              torch.empty((B, D), dtype=torch.float32, pin_memory=True)]
-    outs = [t.numpy() for t in outs_t]
-    nb, nd, no, npi = hb.numpy(), hd.numpy(), ho.numpy(), hp.numpy()
+    pin_in = [pinned(a) for a in (boxes, dims, orient, P_inv)]
+    pin_out = [torch.empty((B, D, 4, 3), dtype=torch.float32, pin_memory=True),
+               torch.empty((B, D, 1, 4), dtype=torch.float32, pin_memory=True),
+               torch.empty((B, D), dtype=torch.float32, pin_memory=True)]
+    outs = [t.numpy() for t in pin_out]
+    nb, nd, no, npi = [t.numpy() for t in pin_in]
+
+    def time_e2e(step, steps):
+        for _ in range(max(1, args.warmup)):
+            step()
+        barrier()
+        e0 = time.time()
+        for _ in range(steps):
+            step()
+        barrier()
+        return max_over_ranks(time.time() - e0)
 
     def e2e_step():
         gpp_b200.fit_road_planes(nb, nd, no, npi, planes, mode=args.mode, device=local_rank, out=outs)
         return float(outs[2][0, 0])                          # the step's result is read on the host
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    barrier()
-    e0 = time.time()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.time() - e0)
+    def e2e_pageable_step():                                 # the drop-in call as the reference's callers make it
+        return float(gpp_b200.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=args.mode, device=local_rank)[2][0, 0])
+
+    e2e_s = time_e2e(e2e_step, args.steps)
     e2e_value = world * hyp_per_step * args.steps / e2e_s
+    pg_steps = max(3, args.steps // 2)
+    e2e_pg_s = time_e2e(e2e_pageable_step, pg_steps)
     h2d = int(nb.nbytes + nd.nbytes + no.nbytes + npi.nbytes)
     d2h = int(sum(o.nbytes for o in outs))
     clocks = sampler.stop(t_clock0, max(t_clock1, time.time()))
+
+    # ---------------- strong scaling (BASELINE.json configs[3]): rank 0's 4096 images sharded over the N ranks
+    strong = None
+    if world > 1:
+        from gpp_b200.sharding import shard_bounds
+        full = make_workload(B, D, planes, seed=3)            # the same batch on every rank; rank r polls its shard
+        b0, b1 = shard_bounds(B, world, rank)
+        ts = [torch.from_numpy(a[b0:b1]).to(dev) for a in full]
+        for _ in range(args.warmup):
+            device_step(ts)
+        barrier()
+        sk = []
+        for _ in range(args.steps):
+            device_step(ts)
+            torch.cuda.synchronize()
+            sk.append(poller.last_kernel_ms())
+        strong_ms = max_over_ranks(sum(sk)) / args.steps
+        sh_in = [pinned(a[b0:b1]) for a in full]
+        sh_np = [t.numpy() for t in sh_in]
+        sh_out = [o[:b1 - b0] for o in outs]
+
+        def strong_e2e_step():
+            gpp_b200.fit_road_planes(sh_np[0], sh_np[1], sh_np[2], sh_np[3], planes, mode=args.mode, device=local_rank, out=sh_out)
+            return float(sh_out[2][0, 0])
+        strong_e2e_s = time_e2e(strong_e2e_step, args.steps) / args.steps
+        t1_kernel = dev_ms / args.steps                      # one GPU polling all 4096 images (the weak leg of this run)
+        t1_e2e = e2e_s / args.steps
+        strong = {'images_total': B, 'images_per_gpu': [shard_bounds(B, world, r)[1] - shard_bounds(B, world, r)[0] for r in range(world)],
+                  'kernel_ms': strong_ms, 'hyp_per_s_kernel': hyp_per_step / (strong_ms * 1e-3),
+                  'e2e_ms': 1e3 * strong_e2e_s, 'hyp_per_s_e2e': hyp_per_step / strong_e2e_s,
+                  'one_gpu_kernel_ms': t1_kernel, 'one_gpu_e2e_ms': 1e3 * t1_e2e,
+                  'efficiency_kernel': t1_kernel / (world * strong_ms), 'efficiency_e2e': t1_e2e / (world * strong_e2e_s),
+                  'what': 'C4 = %d images sharded over %d GPUs, one process per GPU, time = max over ranks; efficiency = '
+                          'T(1 GPU, same run) / (N x T(N GPUs))' % (B, world)}
+
+    # ---------------- the single-process multi-GPU driver (numpy caller on a multi-GPU box), rank 0 while the others wait
+    multi = None
+    n_vis = torch.cuda.device_count()
+    if world > 1:
+        barrier()
+    if rank == 0 and n_vis > 1:
+        devs = list(range(min(n_vis, max(world, 2)))) if world > 1 else list(range(n_vis))
+        for d in devs:
+            gpp_b200.get_poller(d).set_planes(planes)
+        multi = {'devices': len(devs)}
+        for label, ins, out_arrays in (('pinned', (nb, nd, no, npi), outs), ('pageable', (boxes, dims, orient, P_inv), None)):
+            ms = []
+            for i in range(4):
+                c0 = time.time()
+                gpp_b200.fit_road_planes_multi(ins[0], ins[1], ins[2], ins[3], planes, devices=devs, mode=args.mode, out=out_arrays)
+                if i:
+                    ms.append(1e3 * (time.time() - c0))
+            multi[label + '_ms'] = float(np.mean(ms))
+            multi[label + '_hyp_per_s'] = hyp_per_step / (np.mean(ms) * 1e-3)
+            multi[label + '_efficiency_vs_one_gpu_e2e'] = (1e3 * (e2e_s if label == 'pinned' else e2e_pg_s) /
+                                                           (args.steps if label == 'pinned' else pg_steps)) / (len(devs) * np.mean(ms))
+        multi['what'] = 'fit_road_planes_multi: ONE process, one host thread + one handle per GPU, C4 (%d images) sharded' % B
+    if world > 1:
+        barrier()
 
     # ---------------- the other arithmetic modes, for context (kernel only, 3 steps each)
     other_modes = {}
@@ -332,29 +434,36 @@ def main():
                 oms.append(poller.last_kernel_ms())
         other_modes[other] = world * hyp_per_step / (max_over_ranks(float(np.mean(oms))) * 1e-3)
 
-    # ---------------- the smaller configurations of BASELINE.json, for context (N = 1 only; the bench line is C4)
+    # ---------------- the other configurations of BASELINE.json and the reference's own call shape (N = 1 only)
     other_workloads = None
     if rank == 0 and world == 1:
         other_workloads = {}
-        for tag, (img, db) in (('C3_64x100x10k', (64, '10k')), ('C2_1x100x1k', (1, '1k')), ('1x100x22k', (1, '22k'))):
+        for tag, (img, db, nv) in (('C3_64x100x10k', (64, '10k', 100)), ('C2_1x100x1k', (1, '1k', 100)),
+                                   ('single_image_1x100x22k', (1, '22k', 100)),
+                                   ('single_image_15_valid_rows_85_padding', (1, '22k', 15))):
+            from gpp_b200.utils import synthetic
             pl = load_planes(db)
-            wb, wd, wo, wp = make_workload(img, args.dets, pl, seed=11)
+            wb, wd, wo, wp = synthetic.synth_detections(img, args.dets, pl, seed=11, n_valid=nv)
+            wp = wp.astype(np.float32)
             poller.set_planes(pl)
             tw = [torch.from_numpy(a).to(dev) for a in (wb, wd, wo, wp)]
             kms, calls = [], []
-            for i in range(6):
+            for i in range(8):
                 poller.fit_torch(*tw, mode=args.mode)
                 torch.cuda.synchronize()
                 if i:
                     kms.append(poller.last_kernel_ms())
-            for i in range(6):
-                c0 = time.time()
-                gpp_b200.fit_road_planes(wb, wd, wo, wp, pl, mode=args.mode, device=local_rank)
-                if i:
-                    calls.append(time.time() - c0)
+            feed = np.expand_dims(np.asfortranarray(pl.astype(np.float64)), axis=0)     # the callers' (1, N, 4) float64 feed
+            for i in range(30):
+                c0 = time.perf_counter()
+                gpp_b200.fit_road_planes(wb, wd, wo, wp, feed, mode=args.mode, device=local_rank)
+                if i >= 5:
+                    calls.append(time.perf_counter() - c0)
             hyp = float(img) * args.dets * pl.shape[0]
-            other_workloads[tag] = {'kernel_ms': float(np.mean(kms)), 'hyp_per_s_kernel': hyp / (np.mean(kms) * 1e-3),
-                                    'numpy_call_ms': 1e3 * float(np.mean(calls))}
+            k = float(np.median(kms))
+            other_workloads[tag] = {'kernel_ms': k, 'hyp_per_s_kernel': hyp / (k * 1e-3),
+                                    'numpy_call_ms': 1e3 * float(np.median(calls)),
+                                    'roofline_frac': W_ALG * hyp / (k * 1e-3) / 1e12 / peak_tflops}
         poller.set_planes(planes)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
@@ -375,16 +484,8 @@ def main():
                'c_port_sample': '%d images (%.1f s), fused C restatement, all host threads' % (c_img, c_dt),
                'host_cpu_count': os.cpu_count()}
 
-    traffic, traffic_src = None, None
-    import glob
-    tfiles = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic_c4.json')))     # newest capture last
-    tpath = tfiles[-1] if tfiles else ''
-    if args.mode == 'verified' and args.images == 4096 and args.planes == '22k' and tpath:
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # bytes per launch, from the ncu capture
-        traffic_src = 'profiles/%s (ncu --set full capture of this launch)' % os.path.basename(tpath)
     if rank == 0:
+        pipes = ncu_pipe_summary() if (args.mode == 'verified' and args.images == 4096 and args.planes == '22k') else None
         ms_per_step = dev_ms / args.steps
         achieved = W_ALG * value / world / 1e12              # per-GPU TFLOP/s of algorithmic work
         line = {
@@ -395,21 +496,33 @@ def main():
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': 1e3 * e2e_s / args.steps,
                     'api': 'gpp_b200.fit_road_planes (numpy in/out, pinned host buffers) -> gpp_fit_host'},
+            'e2e_pageable': {'value': world * hyp_per_step * pg_steps / e2e_pg_s, 'unit': UNIT,
+                             'ms_per_step': 1e3 * e2e_pg_s / pg_steps, 'steps': pg_steps,
+                             'api': 'gpp_b200.fit_road_planes on plain (pageable) numpy arrays, results in fresh arrays: '
+                                    'the drop-in call'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak_tflops, 'traffic': traffic, 'traffic_unit': 'bytes/launch',
-                         'traffic_source': traffic_src,
+                         'frac': achieved / peak_tflops,
+                         'traffic': pipes['dram_bytes_per_launch'] if pipes else None, 'traffic_unit': 'bytes/launch',
+                         'traffic_source': pipes['source'] if pipes else None,
                          'peak_source': 'libgpp FFMA microbenchmark, same run (MEASURED_PEAKS.json has no FP32 entry)',
                          'nominal_peak': NOMINAL_FP32_TFLOPS, 'frac_of_nominal': achieved / NOMINAL_FP32_TFLOPS,
                          'flop_per_hypothesis': W_ALG, 'kernel': KERNEL_OF_MODE[args.mode],
-                         'kernel_ms_per_launch': ms_per_step},
+                         'kernel_ms_per_launch': ms_per_step,
+                         'fma_pipe_active_pct': pipes['fma_pipe_active_pct'] if pipes else None,
+                         'xu_pipe_pct': pipes['xu_pipe_pct'] if pipes else None,
+                         'issue_active_pct': pipes['issue_active_pct'] if pipes else None,
+                         'pipe_source': pipes['source'] if pipes else None},
             'cpu_baseline': cpu,
             'other_modes': dict(other_modes, unit=UNIT),
             'other_workloads': other_workloads,
+            'strong': strong,
+            'multi_gpu_single_process': multi,
             'wall_ms_per_step_device_leg': 1e3 * wall_dev / args.steps,
             'kernel_ms_steps': [round(x, 3) for x in kernel_ms],
         }
+        line.update(parity or {})
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

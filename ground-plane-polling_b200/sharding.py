@@ -57,12 +57,13 @@ def fit_road_planes_sharded(boxes, dimensions, orientations, P_inv, planes, mode
 
 
 def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, devices=None, mode=None, return_index=False,
-                          fit_fn=None):
+                          fit_fn=None, out=None):
     """``fit_road_planes`` over several GPUs of one box from ONE process: device ``devices[i]`` polls the i-th
     contiguous shard of images (its own handle, stream and copy of the database); one host thread per device drives
     it (the C calls release the GIL) and writes straight into the shard's slice of the result arrays.
 
-    ``devices`` defaults to every visible GPU.  ``planes`` is one database shared by the batch ((N, 4) or (1, N, 4) or
+    ``devices`` defaults to every visible GPU; ``out`` may hold preallocated result arrays for the WHOLE batch (e.g.
+    pinned host memory), each device then writes its shard's slice of them.  ``planes`` is one database shared by the batch ((N, 4) or (1, N, 4) or
     a (B, N, 4) tile of one database).  ``fit_fn(boxes, dims, orient, P_inv, planes, mode=, return_index=, device=,
     out=)`` defaults to ``gpp_b200.fit_road_planes`` (tests inject a stand-in to exercise the host logic on CPU).
     """
@@ -81,14 +82,20 @@ def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, device
     dimensions, orientations, P_inv = np.asarray(dimensions), np.asarray(orientations), np.asarray(P_inv)
     planes = np.asarray(planes)
     if planes.ndim == 3:
-        if planes.shape[0] != 1 and not all(np.array_equal(planes[0], planes[b]) for b in range(1, planes.shape[0])):
+        from .layers.fit_road_planes import _plane_groups
+        if len(_plane_groups(planes, boxes.shape[0])) != 1:
             raise ValueError('fit_road_planes_multi takes one plane database shared by the batch')
         planes = planes[0]
     B, D = boxes.shape[:2]
     out_t = np.float64 if mode == 'f64' else np.float32
-    out = [np.empty((B, D, 4, 3), out_t), np.empty((B, D, 1, 4), out_t), np.empty((B, D), out_t)]
-    if return_index:
-        out.append(np.empty((B, D), np.int64))
+    want = [((B, D, 4, 3), out_t), ((B, D, 1, 4), out_t), ((B, D), out_t)] + ([((B, D), np.int64)] if return_index else [])
+    if out is None:
+        out = [np.empty(shape, dt) for shape, dt in want]
+    else:
+        out = list(out)
+        if len(out) != len(want) or any(not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != dt or
+                                        not a.flags['C_CONTIGUOUS'] for a, (shape, dt) in zip(out, want)):
+            raise ValueError('out must hold C-contiguous arrays of shapes %r' % ([w[0] for w in want],))
     shards = [(dev,) + shard_bounds(B, len(devices), i) for i, dev in enumerate(devices)]
     shards = [s for s in shards if s[2] > s[1]]
 
