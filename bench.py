@@ -250,6 +250,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
             ctypes.CDLL(None).fflush(None)
+            host_group = dist.new_group(backend='gloo')      # host-side waits that leave the GPUs idle (see below)
         finally:
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
@@ -397,10 +398,13 @@ def main():
                           'T(1 GPU, same run) / (N x T(N GPUs))' % (B, world)}
 
     # ---------------- the single-process multi-GPU driver (numpy caller on a multi-GPU box), rank 0 while the others wait
+    # (the other ranks wait in a gloo barrier: an NCCL barrier would keep a spinning kernel of ANOTHER process on
+    # their GPUs, and kernels of two processes time-slice a GPU instead of sharing it)
     multi = None
     n_vis = torch.cuda.device_count()
     if world > 1:
         barrier()
+        dist.barrier(group=host_group)
     if rank == 0 and n_vis > 1:
         devs = list(range(min(n_vis, max(world, 2)))) if world > 1 else list(range(n_vis))
         for d in devs:
@@ -419,6 +423,7 @@ def main():
                                                            (args.steps if label == 'pinned' else pg_steps)) / (len(devs) * np.mean(ms))
         multi['what'] = 'fit_road_planes_multi: ONE process, one host thread + one handle per GPU, C4 (%d images) sharded' % B
     if world > 1:
+        dist.barrier(group=host_group)
         barrier()
 
     # ---------------- the other arithmetic modes, for context (kernel only, 3 steps each)
