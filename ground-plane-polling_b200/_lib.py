@@ -32,6 +32,8 @@ SIGNATURES = {
     'gpp_get_normalised_planes': (c_int, [c_void_p, c_void_p]),
     'gpp_fit_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'gpp_fit_host_multi': (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'gpp_fit_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'gpp_fit_host_f64': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -59,8 +59,9 @@ def fit_road_planes_sharded(boxes, dimensions, orientations, P_inv, planes, mode
 def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, devices=None, mode=None, return_index=False,
                           fit_fn=None, out=None):
     """``fit_road_planes`` over several GPUs of one box from ONE process: device ``devices[i]`` polls the i-th
-    contiguous shard of images (its own handle, stream and copy of the database); one host thread per device drives
-    it (the C calls release the GIL) and writes straight into the shard's slice of the result arrays.
+    contiguous shard of images (its own handle, stream and copy of the database) and writes straight into the shard's
+    slice of the result arrays.  The fan-out runs inside libgpp (``gpp_fit_host_multi``: one C++ host thread per
+    device); an injected ``fit_fn`` is driven by Python threads instead.
 
     ``devices`` defaults to every visible GPU; ``out`` may hold preallocated result arrays for the WHOLE batch (e.g.
     pinned host memory), each device then writes its shard's slice of them.  ``planes`` is one database shared by the batch ((N, 4) or (1, N, 4) or
@@ -68,8 +69,6 @@ def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, device
     out=)`` defaults to ``gpp_b200.fit_road_planes`` (tests inject a stand-in to exercise the host logic on CPU).
     """
     import threading
-    if fit_fn is None:
-        from .layers.fit_road_planes import fit_road_planes as fit_fn
     if devices is None:
         from . import _lib
         devices = list(range(_lib.load().gpp_device_count()))
@@ -96,6 +95,10 @@ def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, device
         if len(out) != len(want) or any(not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != dt or
                                         not a.flags['C_CONTIGUOUS'] for a, (shape, dt) in zip(out, want)):
             raise ValueError('out must hold C-contiguous arrays of shapes %r' % ([w[0] for w in want],))
+    if fit_fn is None and mode != 'f64':
+        return _fit_multi_native(boxes, dimensions, orientations, P_inv, planes, devices, mode, return_index, out)
+    if fit_fn is None:
+        from .layers.fit_road_planes import fit_road_planes as fit_fn
     shards = [(dev,) + shard_bounds(B, len(devices), i) for i, dev in enumerate(devices)]
     shards = [s for s in shards if s[2] > s[1]]
 
@@ -122,4 +125,30 @@ def fit_road_planes_multi(boxes, dimensions, orientations, P_inv, planes, device
             t.join()
         if errors:
             raise errors[0]
+    return out
+
+
+def _fit_multi_native(boxes, dimensions, orientations, P_inv, planes, devices, mode, return_index, out):
+    """The fan-out in C (gpp_fit_host_multi): one ctypes call for the whole batch."""
+    import ctypes
+    from . import _lib
+    from .layers.fit_road_planes import DEFAULT_MODE, _f32, get_poller
+    mode = DEFAULT_MODE if mode is None else mode
+    if mode not in _lib.MODES:
+        raise ValueError('unknown mode %r (expected one of %s)' % (mode, sorted(_lib.MODES)))
+    B, D = boxes.shape[:2]
+    if boxes.shape[2] != 12 or dimensions.shape != (B, D, 3) or orientations.shape != (B, D) or P_inv.shape != (B, 4, 3):
+        raise ValueError('inconsistent shapes: boxes %r dimensions %r orientations %r P_inv %r' % (
+            boxes.shape, dimensions.shape, orientations.shape, P_inv.shape))
+    pollers = [get_poller(d) for d in devices]
+    for p in pollers:
+        p.set_planes(planes)                     # one memcmp per device when the database is the one already resident
+    b, d, p_inv = _f32(boxes), _f32(dimensions), _f32(P_inv)
+    o = np.ascontiguousarray(orientations, dtype=np.int32)
+    handles = (ctypes.c_void_p * len(pollers))(*[p._h for p in pollers])
+    lib = _lib.load()
+    rc = lib.gpp_fit_host_multi(handles, len(pollers), _lib.ptr(b), _lib.ptr(d), _lib.ptr(o), _lib.ptr(p_inv), B, D,
+                                _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+                                _lib.ptr(out[3]) if return_index else None, _lib.MODES[mode])
+    _lib.check(rc, 'gpp_fit_host_multi')
     return out

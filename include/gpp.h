@@ -98,6 +98,14 @@ int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, con
                  const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
                  int64_t *best_index, int mode);
 
+/* The same call over several GPUs of one box (BASELINE.json configs[3]: images sharded, database replicated, results
+ * gathered into one host array): `handles` are n_handles contexts on different devices, each holding the database
+ * (gpp_set_planes on every one).  Image shard i -- contiguous, the first B % n_handles shards one image longer -- is
+ * polled by handles[i] from its own host thread and lands in its slice of the output arrays.  No collective. */
+int gpp_fit_host_multi(gpp_handle **handles, int n_handles, const float *boxes, const float *dimensions,
+                       const int32_t *orientations, const float *P_inv, int B, int D, float *keypoints,
+                       float *keyplanes, float *residuals, int64_t *best_index, int mode);
+
 /* Device entry (the torch / DLPack path): all pointers are device memory on the handle's device; the
  * kernels are enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
  * without synchronising. */
