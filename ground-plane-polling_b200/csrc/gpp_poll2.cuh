@@ -113,13 +113,18 @@ struct PackFast {
     static __device__ __forceinline__ f2 sqrt(f2 a) { return pk(sqrt_approx(lo(a)), sqrt_approx(hi(a))); }
 };
 
-// Error scale of one hypothesis.  Both the fast and the exact fp32 evaluation deviate from the real-valued
-// score mainly through the rounding of t_k = n.d_k (absolute ~u |d_k|) divided by |t_k|: a point at distance
-// |X_k| = |d_k| |d| / |t_k| moves by ~ u |d_k| |X_k| / |t_k| = u |d| (|d_k| i_k)^2 with i_k = 1/|t_k| (quadratic
-// in depth, invariant under a rescaling of the rays), and X_t additionally by ~1/(perp.n).  kMarginK is that first-order scale times a safety factor; the
-// VERIFIED mode is validated against the EXACT mode on full benchmark batches (tests/test_verified_gpu.py).
+// Error margin of one hypothesis (derivation: DESIGN.md section 4.1.1).  Both the fast and the exact fp32 evaluation
+// deviate from the real-valued score mainly through the rounding of t_k = n.d_k (absolute <= ~7 u |d_k| for the two
+// together) divided by |t_k|: a point at distance |X_k| = |d_k| |d| / |t_k| moves by <= ~12 u |d| (|d_k| i_k)^2 with
+// i_k = 1/|t_k| (quadratic in depth, invariant under a rescaling of the rays); the six distances weigh the four points
+// 3 : 3 : 3 : 3, X_t inherits the error of X_m plus that of q ~ 1/(perp.n).  Worst case with every error aligned:
+// 144 u w + 30 u w T/|perp.n| + 24 u |q| T/|perp.n| (w = |d| max_k |d_k|^2 i_max^2), against the margin
+// K u w (1 + T/|perp.n|) + 4 K u |q| T/|perp.n| with K = 128; measured on adversarial inputs (scripts/
+// gpu_margin_pressure.py): |fast - exact| <= 0.11 margin.  Two regions have no first-order bound and are handled
+// separately: t_k at its rounding noise (the margin then exceeds the residual sum itself, so the plane survives) and
+// perp.n at its rounding noise (explicit test in eval_top).
 #ifndef GPP_MARGIN_K
-#define GPP_MARGIN_K 64.0f
+#define GPP_MARGIN_K 128.0f
 #endif
 constexpr float kMarginScale = GPP_MARGIN_K * 5.9604645e-8f;   // K * 2^-24
 
@@ -129,6 +134,7 @@ struct DetConst {
     float T;           // |d_t|^2  (fast formulation only)
     float G;           // d_t . d_m (fast formulation only)
     float ms, msT;     // VERIFIED: K 2^-24 max_k |d_k|^2 and the same times T (margin scales, ray-scale invariant)
+    float msq;         // VERIFIED: 4 K 2^-24 T, scale of the conditioning term of q (see eval_top)
     float fl[2], fm[2], fr[2], ft[2];   // fast formulation: rays rescaled to z = 1, (x, y) only; T, G, ms refer to these
     float mc;          // VERIFIED: 2^-20 * (sum of the six target lengths), see finalize_margin
 };
@@ -147,6 +153,7 @@ __device__ __forceinline__ void fast_constants(DetConst &D, const Detection<Exac
     const float d2 = fmaf(D.fr[0], D.fr[0], fmaf(D.fr[1], D.fr[1], 1.0f));
     D.ms = kMarginScale * fmaxf(fmaxf(d0, d1), fmaxf(d2, D.T));
     D.msT = D.ms * D.T;
+    D.msq = 4.0f * kMarginScale * D.T;
     D.mc = 9.5367431640625e-07f * (fabsf(D.td[0]) + fabsf(D.td[1]) + fabsf(D.td[2]) + fabsf(D.td[3]) + fabsf(D.td[4]) +
                                   fabsf(D.td[5]));
 }
@@ -266,6 +273,18 @@ __device__ __forceinline__ void eval_top(const DetConst &D, f2 n0, f2 n1, f2 n2,
         out.zc = fma2(g.a[2], g.b[0], neg2(mul2(g.a[0], g.b[2])));
     }
     const f2 q = mul2(mul2(g.s1, fma2(u, bc(-D.G), mul2(g.t1, bc(D.T)))), iden);
+    if (kMargin) {
+        // perp.n = T - u^2 cancels when the top ray is nearly parallel to the plane normal: its rounding error
+        // (<= 8 ulp of T) is a RELATIVE error rho = 8 u T / |perp.n| of q, and |q| is not bounded by the depth of X_m then
+        // (|q| <= |X_m| sqrt(T / |perp.n|)).  Found by the adversarial soak of round 2 (steep planes: the term above
+        // was exceeded up to 9-fold by hypotheses with T / |perp.n| > 5000); three residuals carry the error of q.
+        // Where perp.n is down at its own rounding noise (rho' = 32 rho >= 1/4: not even its sign is known) the error
+        // of q has no first-order bound: the margin is infinite there and the plane is always re-evaluated exactly.
+        const f2 rho = mul2(abs2(iden), bc(D.msq));
+        out.m = fma2(abs2(q), rho, out.m);
+        out.m = pk(lo(rho) < 0.25f ? lo(out.m) : __int_as_float(0x7f800000),
+                   hi(rho) < 0.25f ? hi(out.m) : __int_as_float(0x7f800000));
+    }
     // does the plane separate the rays (sign(t_l) or sign(t_r) != sign(t_m)) for any pair of this warp?
     const unsigned sd = ((__float_as_uint(lo(g.t0)) ^ __float_as_uint(lo(g.t1))) | (__float_as_uint(lo(g.t2)) ^ __float_as_uint(lo(g.t1))) |
                          (__float_as_uint(hi(g.t0)) ^ __float_as_uint(hi(g.t1))) | (__float_as_uint(hi(g.t2)) ^ __float_as_uint(hi(g.t1)))) >> 31;

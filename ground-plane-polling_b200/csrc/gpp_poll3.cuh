@@ -69,15 +69,16 @@ __device__ __forceinline__ void store_cold(float *detx, const DetConst &D) {
     float *c = detx + kColdOffset;
     c[0] = D.ft[0]; c[1] = D.ft[1]; c[2] = D.T; c[3] = D.G;
     c[4] = D.msT; c[5] = D.mc; c[6] = D.td[0]; c[7] = D.td[4];
-    c[8] = D.td[5];
+    c[8] = D.td[5]; c[9] = D.msq;
 }
 __device__ __forceinline__ void load_cold(DetConst &D, const float *detx) {
     const uint32_t a = smem_u32(detx + kColdOffset);
-    float x8, pad0, pad1, pad2;
+    float x8, x9, pad1, pad2;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(D.ft[0]), "=f"(D.ft[1]), "=f"(D.T), "=f"(D.G) : "r"(a));
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(D.msT), "=f"(D.mc), "=f"(D.td[0]), "=f"(D.td[4]) : "r"(a));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(x8), "=f"(pad0), "=f"(pad1), "=f"(pad2) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(x8), "=f"(x9), "=f"(pad1), "=f"(pad2) : "r"(a));
     D.td[5] = x8;
+    D.msq = x9;
 }
 
 // (max-votes, best residual) as one 64-bit key that grows when the pair improves: more votes first, then a smaller
