@@ -36,6 +36,10 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'gpp_fit_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'gpp_fit_pose_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'gpp_fit_pose_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'gpp_fit_host_f64': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     'gpp_fit_device_f64': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -57,7 +61,6 @@ SIGNATURES = {
     'gpp_last_kernel_ms': (c_int, [c_void_p, c_float_p]),
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),
-    'gpp_debug_set_config': (c_int, [c_void_p, c_int, c_int]),
     'gpp_debug_set_schedule': (c_int, [c_void_p, c_int, c_int]),
     'gpp_audit_set': (c_int, [c_void_p, c_int]),
     'gpp_audit_counts': (c_int, [c_void_p, c_int64_p, c_int64_p]),

@@ -144,13 +144,6 @@ int gpp_destroy(gpp_handle *h) {
     cudaFree(h->filter_counts);
     gpp::release_poll3(h);
     gpp::release_audit(h);
-    for (auto &w : h->work) {
-        cudaFree(w.list);
-        cudaFree(w.ulist);
-        cudaFree(w.unique);
-        cudaFree(w.count);
-        if (w.done) cudaEventDestroy(w.done);
-    }
     for (int i = 0; i < gpp_handle::kStreams; ++i) {
         h->stage[i].release();
         h->hstage[i].release();
@@ -201,8 +194,6 @@ static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
 // every launch that may still read the resident database has an event on record: wait for them on `s`
 static int wait_for_fits(gpp_handle *h, cudaStream_t s) {
     for (auto &w : h->slot3)
-        if (w.used) GPP_CUDA(cudaStreamWaitEvent(s, w.done, 0));
-    for (auto &w : h->work)
         if (w.used) GPP_CUDA(cudaStreamWaitEvent(s, w.done, 0));
     if (h->audit_used) GPP_CUDA(cudaStreamWaitEvent(s, h->audit_done, 0));
     return GPP_OK;
@@ -296,31 +287,54 @@ static int check_fit_args(const gpp_handle *h, const void *boxes, const void *di
     return GPP_OK;
 }
 
+static bool float_mode(int mode) { return mode == GPP_MODE_EXACT || mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED; }
+
+static int fit_device_impl(gpp_handle *h, const gpp::FitIO &io, int mode, cudaStream_t s) {
+    if (io.n_det == 0) return GPP_OK;
+    DeviceGuard guard(h->device);
+    if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
+    GPP_CUDA(cudaEventRecord(h->ev_start, s));
+    int rc = gpp::launch_poll(h, io, mode, s);
+    if (rc) return rc;
+    GPP_CUDA(cudaEventRecord(h->ev_stop, s));
+    h->timing_chunks = 0;
+    h->timing_single = true;
+    return GPP_OK;
+}
+
 int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
                    const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
                    int64_t *best_index, int mode, void *stream) {
     int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                             "gpp_fit_device");
     if (rc) return rc;
-    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST && mode != GPP_MODE_VERIFIED)
+    if (!float_mode(mode))
         return set_error(GPP_EINVAL, "gpp_fit_device: mode %d (use gpp_fit_device_f64 for the FP64 mode)", mode);
-    if ((long long)B * D == 0) return GPP_OK;
-    DeviceGuard guard(h->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    gpp::PollArgs<float> a;
-    a.boxes = boxes; a.dims = dimensions; a.orient = orientations; a.pinv = P_inv;
-    a.planes = h->d_planes32; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
-    a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
-    a.best = reinterpret_cast<long long *>(best_index);
-    a.det_list = nullptr; a.det_count = nullptr;
-    if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
-    GPP_CUDA(cudaEventRecord(h->ev_start, s));
-    rc = gpp::launch_poll_f32(h, a, mode, s);
+    gpp::FitIO io;
+    io.boxes = boxes; io.dims = dimensions; io.orient = orientations; io.pinv = P_inv;
+    io.D = D; io.n_det = (long long)B * D;
+    io.keypoints = keypoints; io.keyplanes = keyplanes; io.residuals = residuals;
+    io.best = reinterpret_cast<long long *>(best_index);
+    return fit_device_impl(h, io, mode, static_cast<cudaStream_t>(stream));
+}
+
+int gpp_fit_pose_device(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                        const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                        int64_t *best_index, float *locations, float *angles, float *dimensions_out, float *kitti,
+                        int mode, void *stream) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_pose_device");
     if (rc) return rc;
-    GPP_CUDA(cudaEventRecord(h->ev_stop, s));
-    h->timing_chunks = 0;
-    h->timing_single = true;
-    return GPP_OK;
+    if (!float_mode(mode)) return set_error(GPP_EINVAL, "gpp_fit_pose_device: mode %d", mode);
+    if ((long long)B * D > 0 && (!locations || !angles || !dimensions_out))
+        return set_error(GPP_EINVAL, "gpp_fit_pose_device: NULL pose array");
+    gpp::FitIO io;
+    io.boxes = boxes; io.dims = dimensions; io.orient = orientations; io.pinv = P_inv;
+    io.D = D; io.n_det = (long long)B * D;
+    io.keypoints = keypoints; io.keyplanes = keyplanes; io.residuals = residuals;
+    io.best = reinterpret_cast<long long *>(best_index);
+    io.pose_locations = locations; io.pose_angles = angles; io.pose_dimensions = dimensions_out; io.pose_kitti = kitti;
+    return fit_device_impl(h, io, mode, static_cast<cudaStream_t>(stream));
 }
 
 int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimensions,
@@ -329,23 +343,12 @@ int gpp_fit_device_f64(gpp_handle *h, const float *boxes, const float *dimension
     int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                             "gpp_fit_device_f64");
     if (rc) return rc;
-    if ((long long)B * D == 0) return GPP_OK;
-    DeviceGuard guard(h->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    gpp::PollArgs<double> a;
-    a.boxes = boxes; a.dims = dimensions; a.orient = orientations; a.pinv = P_inv;
-    a.planes = h->d_planes64; a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = (long long)B * D;
-    a.keypoints = keypoints; a.keyplanes = keyplanes; a.residuals = residuals;
-    a.best = reinterpret_cast<long long *>(best_index);
-    a.det_list = nullptr; a.det_count = nullptr;
-    if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
-    GPP_CUDA(cudaEventRecord(h->ev_start, s));
-    rc = gpp::launch_poll_f64(h, a, s);
-    if (rc) return rc;
-    GPP_CUDA(cudaEventRecord(h->ev_stop, s));
-    h->timing_chunks = 0;
-    h->timing_single = true;
-    return GPP_OK;
+    gpp::FitIO io;
+    io.boxes = boxes; io.dims = dimensions; io.orient = orientations; io.pinv = P_inv;
+    io.D = D; io.n_det = (long long)B * D;
+    io.keypoints = keypoints; io.keyplanes = keyplanes; io.residuals = residuals;
+    io.best = reinterpret_cast<long long *>(best_index);
+    return fit_device_impl(h, io, GPP_MODE_F64, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
@@ -399,8 +402,8 @@ static bool is_pageable(const void *p) {
 // device staging block and the pinned host staging block use the same layout, so that a staged chunk moves with ONE
 // copy in each direction.
 struct ChunkLayout {
-    size_t o_boxes, o_dims, o_orient, o_pinv, in_end, o_kp, o_kpl, o_res, o_best, o_end;
-    ChunkLayout(size_t n_det, size_t n_img, size_t esz) {
+    size_t o_boxes, o_dims, o_orient, o_pinv, in_end, o_kp, o_kpl, o_res, o_best, o_loc, o_ang, o_pdim, o_kitti, o_end;
+    ChunkLayout(size_t n_det, size_t n_img, size_t esz, bool with_best, bool with_pose, bool with_kitti) {
         auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
         o_boxes = 0;
         o_dims = o_boxes + up(48 * n_det);
@@ -411,14 +414,23 @@ struct ChunkLayout {
         o_kpl = o_kp + up(esz * 12 * n_det);
         o_res = o_kpl + up(esz * 4 * n_det);
         o_best = o_res + up(esz * n_det);
-        o_end = o_best + up(8 * n_det);
+        o_loc = o_best + (with_best ? up(8 * n_det) : 0);
+        o_ang = o_loc + (with_pose ? up(12 * n_det) : 0);
+        o_pdim = o_ang + (with_pose ? up(12 * n_det) : 0);
+        o_kitti = o_pdim + (with_pose ? up(12 * n_det) : 0);
+        o_end = o_kitti + (with_kitti ? up(16 * n_det) : 0);
     }
+};
+
+// optional host outputs of the fused steps after polling
+struct PoseHost {
+    float *locations = nullptr, *angles = nullptr, *dimensions = nullptr, *kitti = nullptr;
 };
 
 template <class T>
 static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, const int32_t *orient,
                          const float *pinv, int B, int D, T *keypoints, T *keyplanes, T *residuals,
-                         int64_t *best, int mode) {
+                         int64_t *best, int mode, const PoseHost &pose = PoseHost()) {
     if ((long long)B * D == 0) return GPP_OK;
     DeviceGuard guard(h->device);
     // chunk size: enough hypotheses to fill the machine a few times over, at most 65,536 detections
@@ -434,7 +446,8 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
     while (start.back() < B) start.push_back(start.back() + imgs_per_chunk < B ? start.back() + imgs_per_chunk : B);
     const int n_chunks = (int)start.size() - 1;
     const int n_streams = n_chunks > 1 ? gpp_handle::kStreams : 1;
-    const ChunkLayout L((size_t)imgs_per_chunk * D, (size_t)imgs_per_chunk, sizeof(T));
+    const bool with_pose = pose.locations != nullptr, with_kitti = with_pose && pose.kitti != nullptr;
+    const ChunkLayout L((size_t)imgs_per_chunk * D, (size_t)imgs_per_chunk, sizeof(T), best != nullptr, with_pose, with_kitti);
     for (int i = 0; i < n_streams; ++i) {
         int rc = h->stage[i].reserve(L.o_end);
         if (rc) return rc;
@@ -451,13 +464,13 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
     const bool small = n_chunks == 1 && (long long)B * D <= 16384;
     const bool staged = small || is_pageable(boxes) || is_pageable(dims) || is_pageable(orient) || is_pageable(pinv) ||
                         is_pageable(keypoints) || is_pageable(keyplanes) || is_pageable(residuals) ||
-                        (best && is_pageable(best));
+                        (best && is_pageable(best)) || (with_pose && (is_pageable(pose.locations) ||
+                        is_pageable(pose.angles) || is_pageable(pose.dimensions))) || (with_kitti && is_pageable(pose.kitti));
     if (staged)
         for (int i = 0; i < n_streams; ++i) {
             int rc = h->hstage[i].reserve(L.o_end);
             if (rc) return rc;
         }
-    const size_t out_end = best ? L.o_end : L.o_best;
     // copies the finished outputs of chunk c from its pinned block to the caller's arrays
     auto drain = [&](int c) -> int {
         const int b0 = start[c], nb = start[c + 1] - start[c];
@@ -468,6 +481,12 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
         memcpy(keyplanes + 4 * m0, hs.base + L.o_kpl, sizeof(T) * 4 * nm);
         memcpy(residuals + m0, hs.base + L.o_res, sizeof(T) * nm);
         if (best) memcpy(best + m0, hs.base + L.o_best, sizeof(long long) * nm);
+        if (with_pose) {
+            memcpy(pose.locations + 3 * m0, hs.base + L.o_loc, sizeof(float) * 3 * nm);
+            memcpy(pose.angles + 3 * m0, hs.base + L.o_ang, sizeof(float) * 3 * nm);
+            memcpy(pose.dimensions + 3 * m0, hs.base + L.o_pdim, sizeof(float) * 3 * nm);
+        }
+        if (with_kitti) memcpy(pose.kitti + 4 * m0, hs.base + L.o_kitti, sizeof(float) * 4 * nm);
         return GPP_OK;
     };
     for (int c = 0; c < n_chunks; ++c) {
@@ -494,25 +513,27 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
             GPP_CUDA(cudaMemcpyAsync(dev + L.o_orient, src_orient, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, s));
             GPP_CUDA(cudaMemcpyAsync(dev + L.o_pinv, src_pinv, sizeof(float) * 12 * nb, cudaMemcpyHostToDevice, s));
         }
-        gpp::PollArgs<T> a;
-        a.boxes = reinterpret_cast<const float *>(dev + L.o_boxes);
-        a.dims = reinterpret_cast<const float *>(dev + L.o_dims);
-        a.orient = reinterpret_cast<const int32_t *>(dev + L.o_orient);
-        a.pinv = reinterpret_cast<const float *>(dev + L.o_pinv);
-        a.planes = sizeof(T) == 8 ? (const void *)h->d_planes64 : (const void *)h->d_planes32;
-        a.n_planes = h->n_planes; a.dets_per_image = D; a.n_det = nm;
-        a.keypoints = reinterpret_cast<T *>(dev + L.o_kp);
-        a.keyplanes = reinterpret_cast<T *>(dev + L.o_kpl);
-        a.residuals = reinterpret_cast<T *>(dev + L.o_res);
-        a.best = best ? reinterpret_cast<long long *>(dev + L.o_best) : nullptr;
-        a.det_list = nullptr; a.det_count = nullptr;
+        gpp::FitIO io;
+        io.boxes = reinterpret_cast<const float *>(dev + L.o_boxes);
+        io.dims = reinterpret_cast<const float *>(dev + L.o_dims);
+        io.orient = reinterpret_cast<const int32_t *>(dev + L.o_orient);
+        io.pinv = reinterpret_cast<const float *>(dev + L.o_pinv);
+        io.D = D; io.n_det = nm;
+        io.keypoints = dev + L.o_kp; io.keyplanes = dev + L.o_kpl; io.residuals = dev + L.o_res;
+        io.best = best ? reinterpret_cast<long long *>(dev + L.o_best) : nullptr;
+        if (with_pose) {
+            io.pose_locations = reinterpret_cast<float *>(dev + L.o_loc);
+            io.pose_angles = reinterpret_cast<float *>(dev + L.o_ang);
+            io.pose_dimensions = reinterpret_cast<float *>(dev + L.o_pdim);
+            io.pose_kitti = with_kitti ? reinterpret_cast<float *>(dev + L.o_kitti) : nullptr;
+        }
         if (h->planes_pending && h->planes_stream != s) GPP_CUDA(cudaStreamWaitEvent(s, h->planes_ready, 0));
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].first, s));
-        int rc = gpp::launch_poll(h, a, mode, s);
+        int rc = gpp::launch_poll(h, io, mode, s);
         if (rc) return rc;
         GPP_CUDA(cudaEventRecord(h->chunk_events[c].second, s));
         if (staged) {
-            GPP_CUDA(cudaMemcpyAsync(hs.base + L.o_kp, dev + L.o_kp, out_end - L.o_kp, cudaMemcpyDeviceToHost, s));
+            GPP_CUDA(cudaMemcpyAsync(hs.base + L.o_kp, dev + L.o_kp, L.o_end - L.o_kp, cudaMemcpyDeviceToHost, s));
             GPP_CUDA(cudaEventRecord(hs.done, s));
         } else {
             GPP_CUDA(cudaMemcpyAsync(keypoints + 12 * m0, dev + L.o_kp, sizeof(T) * 12 * nm, cudaMemcpyDeviceToHost, s));
@@ -520,6 +541,13 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
             GPP_CUDA(cudaMemcpyAsync(residuals + m0, dev + L.o_res, sizeof(T) * nm, cudaMemcpyDeviceToHost, s));
             if (best)
                 GPP_CUDA(cudaMemcpyAsync(best + m0, dev + L.o_best, sizeof(long long) * nm, cudaMemcpyDeviceToHost, s));
+            if (with_pose) {
+                GPP_CUDA(cudaMemcpyAsync(pose.locations + 3 * m0, dev + L.o_loc, sizeof(float) * 3 * nm, cudaMemcpyDeviceToHost, s));
+                GPP_CUDA(cudaMemcpyAsync(pose.angles + 3 * m0, dev + L.o_ang, sizeof(float) * 3 * nm, cudaMemcpyDeviceToHost, s));
+                GPP_CUDA(cudaMemcpyAsync(pose.dimensions + 3 * m0, dev + L.o_pdim, sizeof(float) * 3 * nm, cudaMemcpyDeviceToHost, s));
+            }
+            if (with_kitti)
+                GPP_CUDA(cudaMemcpyAsync(pose.kitti + 4 * m0, dev + L.o_kitti, sizeof(float) * 4 * nm, cudaMemcpyDeviceToHost, s));
         }
     }
     if (staged)
@@ -541,10 +569,26 @@ int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, con
     int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                             "gpp_fit_host");
     if (rc) return rc;
-    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST && mode != GPP_MODE_VERIFIED)
+    if (!float_mode(mode))
         return set_error(GPP_EINVAL, "gpp_fit_host: mode %d (use gpp_fit_host_f64 for the FP64 mode)", mode);
     return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                                 best_index, mode);
+}
+
+int gpp_fit_pose_host(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                      const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                      int64_t *best_index, float *locations, float *angles, float *dimensions_out, float *kitti,
+                      int mode) {
+    int rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                            "gpp_fit_pose_host");
+    if (rc) return rc;
+    if (!float_mode(mode)) return set_error(GPP_EINVAL, "gpp_fit_pose_host: mode %d", mode);
+    if ((long long)B * D > 0 && (!locations || !angles || !dimensions_out))
+        return set_error(GPP_EINVAL, "gpp_fit_pose_host: NULL pose array");
+    PoseHost pose;
+    pose.locations = locations; pose.angles = angles; pose.dimensions = dimensions_out; pose.kitti = kitti;
+    return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
+                                best_index, mode, pose);
 }
 
 // One caller, several GPUs: the images are split into contiguous shards (the first B % n handles get one image more),
@@ -554,8 +598,7 @@ int gpp_fit_host_multi(gpp_handle **handles, int n_handles, const float *boxes, 
                        const int32_t *orientations, const float *P_inv, int B, int D, float *keypoints,
                        float *keyplanes, float *residuals, int64_t *best_index, int mode) {
     if (!handles || n_handles < 1) return set_error(GPP_EINVAL, "gpp_fit_host_multi: no handles");
-    if (mode != GPP_MODE_EXACT && mode != GPP_MODE_FAST && mode != GPP_MODE_VERIFIED)
-        return set_error(GPP_EINVAL, "gpp_fit_host_multi: mode %d", mode);
+    if (!float_mode(mode)) return set_error(GPP_EINVAL, "gpp_fit_host_multi: mode %d", mode);
     for (int i = 0; i < n_handles; ++i) {
         int rc = check_fit_args(handles[i], boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                                 "gpp_fit_host_multi");
@@ -680,14 +723,6 @@ int gpp_audit_counts(gpp_handle *h, int64_t *checked, int64_t *mismatches) {
     }
     if (checked) *checked = (int64_t)c[0];
     if (mismatches) *mismatches = (int64_t)c[1];
-    return GPP_OK;
-}
-
-int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm) {
-    if (!h) return set_error(GPP_EINVAL, "gpp_debug_set_config: handle is NULL");
-    h->force_variant = variant % 100;
-    h->force_split = variant >= 200 ? -1 : (variant >= 100 ? 1 : 0);   // +100: force split kernels, +200: forbid
-    h->force_ctas_per_sm = ctas_per_sm;
     return GPP_OK;
 }
 

@@ -32,32 +32,42 @@ struct HostStaging {
     void release();
 };
 
+// One polling call on device memory: what the reference's operator takes and returns (fit_road_planes.py:49-61,
+// :139) plus the optional extensions (arg-min index; pose and KITTI record of every row).
+struct FitIO {
+    const float *boxes = nullptr, *dims = nullptr, *pinv = nullptr;
+    const int32_t *orient = nullptr;
+    int D = 0;                        // detections per image
+    long long n_det = 0;              // B * D
+    void *keypoints = nullptr, *keyplanes = nullptr, *residuals = nullptr;   // float, or double in the F64 mode
+    long long *best = nullptr;
+    float *pose_locations = nullptr, *pose_angles = nullptr, *pose_dimensions = nullptr, *pose_kitti = nullptr;
+};
+
 }  // namespace gpp
 
 struct gpp_handle {
     static constexpr int kStreams = 2;
     int device = 0;
     int sm_count = 0;
-    // plane database (device): raw upload, normalised fp32 (float4) and fp64 (double4) copies
+    // plane database (device): raw upload, normalised fp32 (float4) and fp64 (double4) copies, pair-interleaved fp32
+    // copy padded to 64 planes (gpp_poll2.cuh)
     float *d_raw = nullptr;
     float4 *d_planes32 = nullptr;
     double4 *d_planes64 = nullptr;
-    // VERIFIED mode: detections deferred to the EXACT second pass.  A small ring of work lists, each guarded
-    // by an event, so that launches in flight on different streams never share one.
-    struct WorkSlot {
-        long long *list = nullptr;       // deferred detections (VERIFIED second pass)
-        long long *ulist = nullptr;      // rows to poll (not a repeat of the previous row of the image)
-        unsigned char *unique = nullptr; // per row: 1 = polled, 0 = copy of an earlier row
-        unsigned int *count = nullptr;   // [0] deferred count, [1] unique count
-        long long cap = 0;
-        cudaEvent_t done = nullptr;
-        bool used = false;
-    };
-    static constexpr int kWorkSlots = 4;
-    WorkSlot work[kWorkSlots];
-    unsigned next_work = 0;
-    // resident-database kernel (gpp_poll3.cuh): self-resetting counters and the scratch of segmented detections, one
-    // set per slot so that launches in flight on different streams never share one
+    unsigned long long *d_pairs = nullptr;
+    int n_pairs_padded = 0;
+    int n_planes = 0, cap_planes = 0;
+    // bytes of the last host upload as the caller passed them (gpp_set_planes_raw compares before doing any work)
+    std::vector<unsigned char> raw_copy;
+    int raw_dtype = 0, raw_order = 0;
+    bool raw_valid = false;
+    // a device-side database update (gpp_set_planes_device) that fits on other streams have to wait for
+    cudaEvent_t planes_ready = nullptr;
+    cudaStream_t planes_stream = nullptr;
+    bool planes_pending = false;
+    // polling kernel (gpp_poll3.cuh): self-resetting counters and the scratch of segmented detections, one set per
+    // slot so that launches in flight on different streams never share one
     struct Slot3 {
         unsigned long long *claim = nullptr;     // [2]
         gpp::SegPartial *partials = nullptr;     // [seg_items_cap]
@@ -76,26 +86,14 @@ struct gpp_handle {
     int audit_every = 0;
     long long audit_cap = 0;
     float *audit_out = nullptr;              // key-points, key-planes, residuals of the audit pass (17 floats per row)
-    long long *audit_best = nullptr, *audit_best_main = nullptr, *audit_list = nullptr;
-    unsigned int *audit_count = nullptr;
+    long long *audit_best = nullptr, *audit_best_main = nullptr;
     unsigned long long *audit_counts = nullptr;   // [0] rows checked, [1] rows that differ
     cudaEvent_t audit_done = nullptr;
     bool audit_used = false;
-    unsigned long long *d_pairs = nullptr;   // pair-interleaved fp32 copy, padded to 64 planes (gpp_poll2.cuh)
-    int n_pairs_padded = 0;
-    int n_planes = 0, cap_planes = 0;
-    // bytes of the last host upload as the caller passed them (gpp_set_planes_raw compares before doing any work)
-    std::vector<unsigned char> raw_copy;
-    int raw_dtype = 0, raw_order = 0;
-    bool raw_valid = false;
-    // a device-side database update (gpp_set_planes_device) that fits on other streams have to wait for
-    cudaEvent_t planes_ready = nullptr;
-    cudaStream_t planes_stream = nullptr;
-    bool planes_pending = false;
     // host-entry plumbing
     cudaStream_t streams[kStreams] = {nullptr, nullptr};
     gpp::Staging stage[kStreams];
-    gpp::HostStaging hstage[kStreams];       // pinned, only allocated when a caller passes pageable memory
+    gpp::HostStaging hstage[kStreams];       // pinned
     std::vector<std::pair<cudaEvent_t, cudaEvent_t> > chunk_events;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     int timing_chunks = 0;
@@ -107,13 +105,6 @@ struct gpp_handle {
     unsigned int *filter_counts = nullptr;
     size_t filter_keys_bytes = 0, filter_orient_bytes = 0;
     int filter_counts_n = 0;
-    // launch configuration (filled by configure_kernels; the force_* fields are a tuning hook)
-    int force_variant = 0, force_ctas_per_sm = 0;
-    int occ[3] = {0, 0, 0};                      // resident CTAs per SM: exact dpw 1, exact dpw 2, fp64
-    int occ2[3] = {0, 0, 0};                     // fast kernel: [register-budget variant]
-    int occ3[3] = {0, 0, 0};                        // verified kernel: [register-budget variant]
-    int occ_split[4] = {0, 0, 0, 0};             // small-batch (one detection per CTA) kernels: exact, fast, verified, f64
-    int force_split = 0;                         // tuning hook: > 0 force the small-batch kernels, < 0 forbid them
 };
 
 namespace gpp {
@@ -121,17 +112,11 @@ namespace gpp {
 int configure_kernels(gpp_handle *h);
 void release_poll3(gpp_handle *h);
 void release_audit(gpp_handle *h);
-int launch_poll_f32(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s);
 int build_pairs(gpp_handle *h, cudaStream_t s);
+// one polling call (any GPP_MODE_*) on device memory, enqueued on `s`; VERIFIED calls are followed by the audit pass
+// when the handle asks for it
+int launch_poll(gpp_handle *h, const FitIO &io, int mode, cudaStream_t s);
 int launch_scores(gpp_handle *h, const float *d_det, const int32_t *d_orient, int which, int32_t *votes,
                   float *resid, int32_t *zneg, float *margin, cudaStream_t s);
-int launch_poll_f64(gpp_handle *h, const PollArgs<double> &a, cudaStream_t s);
-inline int launch_poll(gpp_handle *h, const PollArgs<float> &a, int mode, cudaStream_t s) {
-    return launch_poll_f32(h, a, mode, s);
-}
-inline int launch_poll(gpp_handle *h, const PollArgs<double> &a, int, cudaStream_t s) {
-    return launch_poll_f64(h, a, s);
-}
 
 }  // namespace gpp
-

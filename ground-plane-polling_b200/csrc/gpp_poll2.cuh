@@ -1,4 +1,4 @@
-// Packed-pair polling kernel (fp32 modes).
+// Packed-pair arithmetic of the FAST and VERIFIED modes (the kernel that drives it is gpp_poll3.cuh).
 //
 // Blackwell's FP32 pipe executes packed two-wide instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 /
 // FMUL2 / FFMA2): a packed add or multiply delivers two IEEE-rounded results per issue slot and a packed FMA
@@ -13,12 +13,6 @@
 // counting by three FMNMX3.
 #pragma once
 #include "gpp_poll.cuh"
-
-#ifndef GPP_M6_UNROLL
-#define GPP_M6_UNROLL 1
-#endif
-#define GPP_PRAGMA_(x) _Pragma(#x)
-#define GPP_UNROLL(n) GPP_PRAGMA_(unroll n)
 
 namespace gpp {
 
@@ -358,28 +352,6 @@ struct LaneBest {
     }
 };
 
-template <class T>
-struct PollArgs2 {
-    const float *boxes, *dims, *pinv;
-    const int32_t *orient;
-    const u64 *pairs;            // pair-interleaved normalised DB: per pair {a0,a1,b0,b1,c0,c1,d0,d1}
-    const float4 *planes;        // plain normalised DB (N x float4), for the epilogue
-    int n_planes;                // N
-    int n_pairs_padded;          // multiple of 32 (database padded to 64 planes with copies of the last)
-    int dets_per_image;
-    long long n_det;
-    T *keypoints, *keyplanes, *residuals;
-    long long *best;
-    // optional work list: process det_list[0 .. *det_count) instead of 0 .. n_det (rows that repeat the
-    // previous row of their image -- FilterDetections' -1 padding -- are computed once and copied)
-    const long long *det_list;
-    const unsigned int *det_count;
-    // dynamic scheduling: detection groups are claimed from this device counter (zeroed before the launch), so
-    // CTAs that drew cheap detections take more groups instead of idling at the end of the kernel
-    unsigned int *group_counter;
-};
-
-// kTile planes per smem tile (multiple of 64), one detection per warp.
 // exact scalar evaluation of one plane of a pair (VERIFIED mode: general path, re-evaluation, epilogue)
 __device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n0, float n1, float n2, float d4,
                                           int &V, float &R, bool &zneg) {
@@ -388,16 +360,6 @@ __device__ __forceinline__ void exact_one(const Detection<ExactF32> &de, float n
 }
 
 constexpr int kVerifyQueue = 96;
-
-// development counters (only with -DGPP_STATS; printed by launch_poll_f32): rows in the all-six phase, rows in
-// the general phase with Mcur >= 4 / < 4, rows that passed the cheap test (all-six, general), exact
-// verifications, flushes, detections
-#ifdef GPP_STATS
-__device__ unsigned long long g_stats[8];
-#define GPP_STAT(i, n) (st_cnt[i] += (n))
-#else
-#define GPP_STAT(i, n) ((void)0)
-#endif
 
 // VERIFIED: exact re-evaluation of one queued plane with the full (max-votes, residual, index) bookkeeping;
 // ties break by index explicitly (the queue is not drained in index order)
@@ -444,520 +406,6 @@ __device__ __forceinline__ int strict_votes(const PairResult &h, bool upper) {
         v += int(fabsf(rk) + mk <= thr);
     }
     return v;
-}
-
-// kVerified: FAST arithmetic is only a filter -- every hypothesis that could be the arg-min within the error
-// margin is re-evaluated in the EXACT arithmetic and all selection state is kept in exact values, so the
-// result equals the EXACT mode's (see the header comment of the verified path below).
-// kSplit: small-batch variant (one detection per CTA, warp w takes the rows r = w (mod kWarps) of every tile).
-// kVMode: 0 = plain FAST search, 1 = VERIFIED.  The verified filter has two warp-uniform phases: while the
-// warp's exact max-votes is below 6 it counts the votes that are possible within the margin (general phase);
-// once a plane with six exact votes is known it tests max_k |r_k| - m <= 0.7 (all-six-votes phase).
-// kFree (VERIFIED, not kSplit): no detection groups and no CTA barrier.  Every warp claims its detections from the
-// device counter on its own and starts each one at whatever tile the CTA's ring currently delivers (the database
-// is scanned in rotated order, which the explicit index tie-breaks of the exact bookkeeping allow); the ring runs
-// as long as any warp needs tiles (`need_until`), warps that ran out of work keep releasing tiles until all are done.
-template <class PP, int kWarps, int kTile, int kStages, int kMinBlocks, int kVMode = 0, bool kSplit = false,
-          bool kFree = false>
-__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) poll2_kernel(const PollArgs2<float> args) {
-    static_assert(!kFree || (kVMode != 0 && !kSplit), "kFree is implemented for the VERIFIED batch kernel");
-    constexpr bool kVerified = kVMode != 0;
-    constexpr int kTilePairs = kTile / 2;
-    constexpr int kRowStep = kSplit ? kWarps : 1;
-    constexpr uint32_t kPairBytes = 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ulonglong2 *tiles = reinterpret_cast<ulonglong2 *>(smem_raw);             // 2 x ulonglong2 per pair
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(kPairBytes) * kStages * kTilePairs);
-    uint64_t *empty_bar = full_bar + kStages;
-    // VERIFIED: per-warp queue of plane indices that survived the fast filter (at most 31 + 64 entries)
-    int *queue = reinterpret_cast<int *>(empty_bar + kStages) + (threadIdx.x >> 5) * kVerifyQueue;
-    WarpPartial<float> *partial = reinterpret_cast<WarpPartial<float> *>(
-        reinterpret_cast<int *>(empty_bar + kStages) + kWarps * kVerifyQueue);              // [2][kWarps], kSplit only
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int N = args.n_planes;
-    const int NP = args.n_pairs_padded;
-    const int n_tiles = (NP + kTilePairs - 1) / kTilePairs;
-    const long long n_work = args.det_list ? (long long)(*args.det_count) : args.n_det;
-    const long long n_groups = kSplit ? n_work : (n_work + kWarps - 1) / kWarps;
-    unsigned int *claim = reinterpret_cast<unsigned int *>(partial + 2 * kWarps);       // [2]: groups k, k+1
-    float *detx = reinterpret_cast<float *>(claim + 2) + (threadIdx.x >> 5) * 20;       // this warp's exact constants
-    // kFree: one past the last tile sequence number any warp has announced it needs / warps that still have work
-    static_assert((size_t(32) * kStages * kTilePairs + 2 * kStages * sizeof(uint64_t) + sizeof(int) * kWarps * kVerifyQueue +
-                   2 * kWarps * sizeof(WarpPartial<float>) + 2 * sizeof(unsigned int) + sizeof(float) * 20 * kWarps) % 8 == 0,
-                  "need_until must be 8-byte aligned");
-    unsigned long long *need_until = reinterpret_cast<unsigned long long *>(reinterpret_cast<float *>(claim + 2) + kWarps * 20);
-    int *active = reinterpret_cast<int *>(need_until + 1);
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kWarps);
-        }
-        mbar_fence_init();
-        if (kFree) {
-            *need_until = 0ull;
-            *active = kWarps;
-        } else {
-            claim[0] = atomicAdd(args.group_counter, 1u);
-            claim[1] = atomicAdd(args.group_counter, 1u);
-        }
-    }
-    __syncthreads();
-
-    auto issue = [&](long long it) {
-        const int s = int(it % kStages);
-        const int t = int(it % n_tiles);
-        const int cnt = min(kTilePairs, NP - t * kTilePairs);
-        const uint32_t bytes = uint32_t(cnt) * kPairBytes;
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        tma_load_1d(reinterpret_cast<unsigned char *>(tiles) + size_t(s) * kTilePairs * kPairBytes,
-                    reinterpret_cast<const unsigned char *>(args.pairs) + size_t(t) * kTilePairs * kPairBytes, bytes,
-                    &full_bar[s]);
-    };
-    // producer state (thread 0 only): tiles issued so far / tiles known to be needed (groups claimed so far)
-    long long issued = 0, known_tiles = 0;
-    auto pump = [&](long long max_index) {
-        while (issued < known_tiles && issued <= max_index) {
-            if (issued >= kStages)                                   // the slot's previous tile must be released
-                mbar_wait(&empty_bar[issued % kStages], uint32_t(((issued / kStages) - 1) & 1));
-            issue(issued);
-            ++issued;
-        }
-    };
-
-    auto pump_free = [&](long long max_index) {                     // kFree: bounded by the announced need instead
-        const long long need = (long long)*reinterpret_cast<volatile unsigned long long *>(need_until);
-        while (issued < need && issued <= max_index) {
-            if (issued >= kStages)
-                mbar_wait(&empty_bar[issued % kStages], uint32_t(((issued / kStages) - 1) & 1));
-            issue(issued);
-            ++issued;
-        }
-    };
-
-    long long it = 0;
-    unsigned int next_claim = 0;
-    if (kFree) {
-        if (lane == 0) next_claim = atomicAdd(args.group_counter, 1u);
-        next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
-    }
-    for (long long k = 0;; ++k) {
-        long long w_id;
-        if (kFree) {
-            const unsigned int cur = next_claim;
-            if ((long long)cur >= n_work) break;                         // warp-uniform: this warp retires
-            if (lane == 0) {
-                atomicMax(need_until, (unsigned long long)(it + n_tiles));   // announced before anything waits for it
-                next_claim = atomicAdd(args.group_counter, 1u);              // claimed one detection ahead
-            }
-            next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
-            w_id = cur;
-        } else {
-            const unsigned int g32 = claim[k & 1], g_next = claim[(k + 1) & 1];
-            if (g32 >= n_groups) break;                                  // CTA-uniform
-            __syncthreads();                                             // everyone has read claim[k & 1]
-            if (threadIdx.x == 0) {
-                claim[k & 1] = atomicAdd(args.group_counter, 1u);        // group k + 2
-                known_tiles = (k + 1 + (g_next < n_groups ? 1 : 0)) * n_tiles;
-                pump(it - 1 + kStages);
-            }
-            const long long g = g32;
-            w_id = kSplit ? g : g * kWarps + warp;
-        }
-        // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
-        long long mm = w_id < n_work ? w_id : n_work - 1;          // tail warps redo the last one
-        if (args.det_list) mm = args.det_list[mm];
-        const long long m = w_id < n_work ? mm : args.n_det;       // >= n_det: nothing is written
-        // The exact per-detection constants are only needed by the rare exact paths (verification batches, the
-        // epilogue): they are parked in this warp's shared-memory slot and re-read there (GPP_LOAD_DET) instead
-        // of occupying 18 registers in the loop.
-#define GPP_LOAD_DET(det)                                                                   \
-    Detection<ExactF32> det;                                                                \
-    _Pragma("unroll") for (int i_ = 0; i_ < 3; ++i_) {                                      \
-        det.dl[i_] = detx[i_]; det.dm[i_] = detx[3 + i_]; det.dr[i_] = detx[6 + i_]; det.dt[i_] = detx[9 + i_]; \
-    }                                                                                       \
-    _Pragma("unroll") for (int i_ = 0; i_ < 6; ++i_) det.td[i_] = detx[12 + i_]
-        DetConst D;
-        {
-            Detection<ExactF32> det0;
-            load_detection<ExactF32, ExactF32>(det0, args.boxes + 12 * mm, args.dims + 3 * mm, __ldg(args.orient + mm),
-                                               args.pinv + 12 * (mm / args.dets_per_image));
-#pragma unroll
-            for (int i = 0; i < 6; ++i) D.td[i] = det0.td[i];
-            fast_constants(D, det0);
-            __syncwarp();                            // the previous detection's readers are done
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    detx[i] = det0.dl[i]; detx[3 + i] = det0.dm[i]; detx[6 + i] = det0.dr[i]; detx[9 + i] = det0.dt[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) detx[12 + i] = det0.td[i];
-            }
-            __syncwarp();
-        }
-
-        LaneState<float> st;                 // general mode (max votes not yet known to be 6)
-        st.reset(FLT_MAX);
-        LaneBest b6;                         // M == 6 mode
-        b6.bestR = FLT_MAX; b6.bestIdx = 0;
-        bool m6 = false;
-        float wbest = FLT_MAX;               // VERIFIED: warp-wide best EXACT residual so far (warp-uniform)
-        float wthr = __int_as_float(0x7f800000);   // VERIFIED: (wbest + mc)(1 + 2^-18), see the all-six phase
-        int qn = 0;                          // VERIFIED: survivors waiting in this warp's queue (warp-uniform)
-        int Mcur = -1;                       // VERIFIED: exact max-votes so far in this warp (warp-uniform)
-#ifdef GPP_STATS
-        unsigned int st_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 1};
-#endif
-
-        for (int tt = 0; tt < n_tiles; ++tt, ++it) {
-            const int t = kFree ? int(it % n_tiles) : tt;            // kFree: wherever the ring is
-            const int s = int(it % kStages);
-            if (kFree && threadIdx.x == 0) pump_free(it - 1 + kStages);   // tile `it` itself may not be issued yet
-            mbar_wait(&full_bar[s], uint32_t((it / kStages) & 1));
-            const ulonglong2 *tile = tiles + size_t(s) * kTilePairs * 2;
-            const int rows = min(kTilePairs, NP - t * kTilePairs) >> 5;
-            const int base_pair = t * kTilePairs;
-            int r = kSplit ? warp : 0;
-            if (!kVerified && !m6) {
-#pragma unroll 1
-                for (; r < rows; r += kRowStep) {
-                    const int p = (r << 5) + lane;
-                    const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
-                    const int j = 2 * (base_pair + p);
-                    {
-                        PairResult h;
-                        eval_pair<false>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                        const f2 R = resid_sum(h);
-                        const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
-                        const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-                        st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
-                        st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
-                    }
-                    if (((r / kRowStep) & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
-                        m6 = true;                               // warp-uniform decision
-                        r += kRowStep;
-                        break;
-                    }
-                }
-                if (m6) {
-                    // candidates found under a lower running max are masked from now on
-                    b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
-                    b6.bestIdx = st.bestIdx;
-                    wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
-                }
-            }
-GPP_UNROLL(GPP_M6_UNROLL)
-            for (; r < rows; r += kRowStep) {
-                const int p = (r << 5) + lane;
-                const ulonglong2 v0 = tile[2 * p], v1 = tile[2 * p + 1];
-                PairResult h;
-                const int j = 2 * (base_pair + p);
-                if (kVerified) {
-                    // ---- filter.  A plane survives iff, within its error margin m, it could matter:
-                    //   all-six phase (Mcur == 6): it has six votes, passes the z-check and scores no worse than
-                    //                              the warp's best exact residual so far;
-                    //   general phase (Mcur < 6):  it may have MORE votes than the exact max-votes so far, or as
-                    //                              many and pass the z-check and score no worse than the best.
-                    // Comparisons are written so that NaN (degenerate fast arithmetic) always survives.
-                    bool trig0, trig1, urgent = false;
-                    if (Mcur == 6) {
-                        // the residual test comes first: once the warp's best is good, almost no pair passes it,
-                        // and the vote / z-check tests (and z_dir_check itself) are skipped for the whole warp.
-                        // skip iff R (1 - 2^-20) - m_geo - mc > wbest; tested as R - m_geo > wthr with the
-                        // warp-uniform wthr = (wbest + mc)(1 + 2^-18), which implies it (m_geo >= 0)
-                        GPP_STAT(0, 1);
-                        const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
-                        // stage 1: the bottom face only (three of the six residuals, nothing that involves X_t).  Their
-                        // sum is a lower bound of the residual sum, and the part of the margin that belongs to the
-                        // points on the plane (w ms <= m_geo) bounds its error: ~3 of 4 iterations end here.
-                        Bottom g;
-                        eval_bottom<true, true>(D, n0, n1, n2, d4, g);
-                        h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
-                        h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
-                        h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
-                        const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
-                        {
-                            const f2 Slo = fma2(neg2(g.w), bc(D.ms), S3);
-                            if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) continue;
-                        }
-                        GPP_STAT(3, 1);
-                        // stage 2: X_t, the height and the two slanted edges, the full margin
-                        f2 ne, nf;
-                        eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
-                        h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
-                        h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
-                        const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
-                        const f2 Rlo = sub2(R, h.m);
-                        trig0 = !(lo(Rlo) > wthr);
-                        trig1 = !(hi(Rlo) > wthr);
-                        if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
-                        h.m = add2(h.m, bc(D.mc));
-                        finalize_margin(h, R, D);
-                        const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                                         rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
-                        const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
-                        // a best residual sum above 0.7 also lets planes with fewer than six votes through the
-                        // residual test: drop them before the z-check / queue work
-                        trig0 = trig0 && !(lo(rlo) > 0.7f);
-                        trig1 = trig1 && !(hi(rlo) > 0.7f);
-                        if (!__any_sync(0xffffffffu, trig0 || trig1)) continue;
-                        h.finish_zc();
-                        const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
-                        const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
-                        {
-                            // A plane that CERTAINLY has six votes and passes the z-check bounds the final best
-                            // residual by its own upper bound R + m: lower the threshold right away instead of
-                            // waiting for the next exact batch (the plane itself stays queued and is verified).
-                            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
-                            const f2 rhi = add2(rm, h.m);
-                            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
-                            const float e0 = (lo(rhi) <= 0.7f && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX) ? lo(Rhi) : FLT_MAX;
-                            const float e1 = (hi(rhi) <= 0.7f && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX) ? hi(Rhi) : FLT_MAX;
-                            const float e = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(e0, e1))));
-                            if (e < wbest) {
-                                wbest = e;
-                                wthr = (wbest + D.mc) * 1.0000038f;
-                            }
-                        }
-                        trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
-                        trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
-                    } else {
-                        GPP_STAT(Mcur >= 4 ? 1 : 2, 1);
-                        eval_pair_fast<false, 1, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                        const f2 R = resid_sum(h);
-                        finalize_margin(h, R, D);
-                        const f2 Rlo = sub2(R, h.m);
-                        if (Mcur >= 4) {
-                            // cheap necessary condition first (warp-uniform skip, like the all-six phase).  With
-                            // p_i = max(|r_2i|, |r_2i+1|):  six votes => max p <= thr,  >= five votes => median p <= thr
-                            // (at most one residual, hence at most one pair, exceeds),  >= four votes => min p <= thr.
-                            // The pair matters only if it may have MORE votes than Mcur, or as many and a residual
-                            // sum no worse than the best.
-                            const f2 p0 = pk(fmaxf(fabsf(lo(h.r[0])), fabsf(lo(h.r[1]))), fmaxf(fabsf(hi(h.r[0])), fabsf(hi(h.r[1]))));
-                            const f2 p1 = pk(fmaxf(fabsf(lo(h.r[2])), fabsf(lo(h.r[3]))), fmaxf(fabsf(hi(h.r[2])), fabsf(hi(h.r[3]))));
-                            const f2 p2 = pk(fmaxf(fabsf(lo(h.r[4])), fabsf(lo(h.r[5]))), fmaxf(fabsf(hi(h.r[4])), fabsf(hi(h.r[5]))));
-                            const f2 pmax = pk(max3f(lo(p0), lo(p1), lo(p2)), max3f(hi(p0), hi(p1), hi(p2)));
-                            const f2 pmin = pk(fminf(fminf(lo(p0), lo(p1)), lo(p2)), fminf(fminf(hi(p0), hi(p1)), hi(p2)));
-                            const f2 pmed = pk(fmaxf(fminf(lo(p0), lo(p1)), fminf(fmaxf(lo(p0), lo(p1)), lo(p2))),
-                                               fmaxf(fminf(hi(p0), hi(p1)), fminf(fmaxf(hi(p0), hi(p1)), hi(p2))));
-                            const f2 more = sub2(Mcur == 5 ? pmax : pmed, h.m);      // > 0.7: cannot have more votes
-                            const f2 same = sub2(Mcur == 5 ? pmed : pmin, h.m);      // > 0.7: cannot have as many
-                            const bool nan0 = !(lo(R) == lo(R)), nan1 = !(hi(R) == hi(R));   // degenerate: full test
-                            const bool may0 = nan0 || !(lo(more) > 0.7f) || (!(lo(same) > 0.7f) && !(lo(Rlo) > wbest));
-                            const bool may1 = nan1 || !(hi(more) > 0.7f) || (!(hi(same) > 0.7f) && !(hi(Rlo) > wbest));
-                            if (!__any_sync(0xffffffffu, may0 || may1)) continue;
-                        }
-                        GPP_STAT(4, 1);
-                        h.finish_zc();
-                        const f2 zhi = z_upper(h, D);
-                        const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
-                        const bool k0 = V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
-                        const bool k1 = V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
-                        if (Mcur >= 4 && __any_sync(0xffffffffu, k0 || k1)) {
-                            // same early bound as in the all-six phase: exactly Mcur votes for certain, z-check passed
-                            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
-                            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
-                            const bool c0 = k0 && strict_votes(h, false) == Mcur && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX;
-                            const bool c1 = k1 && strict_votes(h, true) == Mcur && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX;
-                            const float e = __uint_as_float(__reduce_min_sync(
-                                0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
-                            wbest = fminf(wbest, e);
-                        }
-                        trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
-                        trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
-                        urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
-                    }
-                    const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
-                    const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
-                    if (b0 | b1) {
-                        // ---- queue the survivors; the whole warp re-evaluates them 32 at a time (exact)
-                        const unsigned below = (1u << lane) - 1u;
-                        if (q0) queue[qn + __popc(b0 & below)] = j;
-                        qn += __popc(b0);
-                        if (q1) queue[qn + __popc(b1 & below)] = j + 1;
-                        qn += __popc(b1);
-                        __syncwarp();
-                        const bool flush_all = __any_sync(0xffffffffu, urgent);
-                        if (qn >= 32 || flush_all) {
-                            GPP_STAT(6, 1);
-                            GPP_STAT(5, qn);
-                            GPP_LOAD_DET(det);
-                            while (qn >= 32) {
-                                qn -= 32;
-                                verify_general(det, args.planes, queue[qn + lane], st);
-                            }
-                            if (flush_all && qn > 0) {
-                                if (lane < qn) verify_general(det, args.planes, queue[lane], st);
-                                qn = 0;
-                            }
-                            __syncwarp();
-                            const int Mnew = __reduce_max_sync(0xffffffffu, st.M);
-                            const float wnew = __uint_as_float(__reduce_min_sync(
-                                0xffffffffu, __float_as_uint(st.M == Mnew ? st.bestR : FLT_MAX)));
-                            wbest = (Mnew == Mcur) ? fminf(wbest, wnew) : wnew;   // early bounds stay valid at the same max-votes
-                            Mcur = Mnew;
-                            wthr = (wbest + D.mc) * 1.0000038f;
-                        }
-                    }
-                } else {
-                    // two stages like the VERIFIED all-six phase: the three bottom-face residuals first; their sum never
-                    // exceeds the full sum (floating-point addition of non-negative terms is monotone), so leaving
-                    // here decides exactly what the full test below would decide
-                    const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
-                    Bottom g;
-                    eval_bottom<true, false>(D, n0, n1, n2, d4, g);
-                    h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
-                    h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
-                    h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
-                    {
-                        const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
-                        if (!__any_sync(0xffffffffu, !(lo(S3) > wbest) || !(hi(S3) > wbest))) continue;
-                    }
-                    f2 ne, nf;
-                    eval_top<0, true>(D, n0, n1, n2, d4, g, h, ne, nf);
-                    h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
-                    h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
-                    const f2 R = resid_sum(h);
-                    // only a pair that scores no worse than the warp's best so far can change the result
-                    if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
-                        h.finish_zc();
-                        b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                                   lo(h.zc), lo(R), j);
-                        b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])),
-                                   hi(h.zc), hi(R), j + 1);
-                        wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (!kFree && threadIdx.x == 0) pump(it - 1 + kStages);   // skewed by one tile: rarely waits for the slowest warp
-            __syncwarp();
-        }
-
-        GPP_LOAD_DET(det);                           // exact constants for the rest of this detection
-        if (kVerified) {
-            GPP_STAT(5, qn);
-            if (lane < qn) verify_general(det, args.planes, queue[lane], st);   // the last partial batch
-#ifdef GPP_STATS
-            if (lane == 0)
-                for (int i = 0; i < 8; ++i) atomicAdd(&g_stats[i], (unsigned long long)st_cnt[i]);
-#endif
-            qn = 0;
-            __syncwarp();
-            m6 = false;                              // the epilogue takes (max-votes, best) from `st`
-        }
-        // ---- epilogue: warp reduction, lazy first-masked search, exact recompute of the winner
-        int Mw;
-        float rbest;
-        int idx;
-        if (m6) {
-            Mw = 6;
-            rbest = b6.bestR;
-            idx = b6.bestIdx;
-        } else {
-            Mw = __reduce_max_sync(0xffffffffu, st.M);
-            rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
-            idx = st.bestIdx;
-        }
-        rbest = warp_min_first(rbest, idx);
-        if (kSplit) {
-            // merge the warps' partial results (double-buffered by group parity: one barrier per group)
-            WarpPartial<float> *buf = partial + (k & 1) * kWarps;
-            if (lane == 0) { buf[warp].r = rbest; buf[warp].M = Mw; buf[warp].idx = idx; }
-            __syncthreads();
-            if (warp != 0) continue;
-            const int Ml = lane < kWarps ? buf[lane].M : -1;
-            Mw = __reduce_max_sync(0xffffffffu, Ml);
-            rbest = (lane < kWarps && Ml == Mw) ? buf[lane].r : FLT_MAX;
-            idx = lane < kWarps ? buf[lane].idx : 0;
-            rbest = warp_min_first(rbest, idx);
-        }
-        const bool have_cand = rbest < FLT_MAX;
-        bool sentinel = false;
-        if (!(rbest < 100.0f)) {
-            int first_masked = -1;
-            for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
-                const int p = p0 + lane;                         // pair index; the padded DB covers it
-                const ulonglong2 v0 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p];
-                const ulonglong2 v1 = reinterpret_cast<const ulonglong2 *>(args.pairs)[2 * p + 1];
-                int V0, V1;
-                bool z0, z1;
-                if (kVerified) {
-                    const f2 a01 = from_u64(v0.x), b01 = from_u64(v0.y), c01 = from_u64(v1.x), d01 = from_u64(v1.y);
-                    float Rx;
-                    exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V0, Rx, z0);
-                    exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V1, Rx, z1);
-                } else {
-                    PairResult h;
-                    eval_pair<false>(PP(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                    V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
-                    V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-                    z0 = lo(h.zc) < 0.0f;
-                    z1 = hi(h.zc) < 0.0f;
-                }
-                const bool mk0 = (2 * p < N) && ((V0 < Mw) || z0);
-                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || z1);
-                const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
-                if (b0 | b1) {
-                    const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
-                    const int f1 = b1 ? 2 * (p0 + __ffs(b1) - 1) + 1 : 0x7fffffff;
-                    first_masked = min(f0, f1);
-                }
-            }
-            if (first_masked >= 0) {
-                if (!have_cand || 100.0f < rbest || (100.0f == rbest && first_masked < idx)) {
-                    sentinel = true;
-                    idx = first_masked;
-                }
-            } else if (!have_cand) {
-                idx = 0;
-            }
-        }
-        if (m < args.n_det && lane == 0) {
-            const float4 pl = args.planes[idx];
-            float X[4][3];
-            int V; float R; bool zneg;
-            hypothesis<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
-            const float rr = sentinel ? 100.0f : R;
-            float *kp = args.keypoints + 12 * m;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) kp[3 * k + i] = X[k][i];
-            float *kpl = args.keyplanes + 4 * m;
-            kpl[0] = pl.x; kpl[1] = pl.y; kpl[2] = pl.z; kpl[3] = pl.w;
-            args.residuals[m] = __fdiv_rn(rr, 6.0f);
-            if (args.best) args.best[m] = idx;
-        }
-    }
-    if (kFree) {
-        // ---- out of work: keep releasing the tiles the other warps still stream, leave when nobody needs any
-        __syncwarp();
-        if (lane == 0) atomicSub(active, 1);          // every announcement of this warp precedes this
-        for (;;) {
-            const long long need = (long long)*reinterpret_cast<volatile unsigned long long *>(need_until);
-            if (it < need) {
-                const int s = int(it % kStages);
-                if (threadIdx.x == 0) pump_free(it - 1 + kStages);
-                mbar_wait(&full_bar[s], uint32_t((it / kStages) & 1));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                ++it;
-                continue;
-            }
-            if (*reinterpret_cast<volatile int *>(active) == 0) {
-                __threadfence_block();
-                if (it >= (long long)*reinterpret_cast<volatile unsigned long long *>(need_until)) break;
-            } else {
-                __nanosleep(500);
-            }
-        }
-    }
 }
 
 }  // namespace gpp

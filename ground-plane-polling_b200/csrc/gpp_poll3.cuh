@@ -1,4 +1,4 @@
-// Resident-database polling kernel of the packed fp32 modes (FAST, VERIFIED) -- the default since round 2.
+// The polling kernel (all four arithmetic modes) -- since round 2 the only one.
 //
 // The ring kernels (gpp_poll2.cuh) stream the database through ONE tile ring per CTA, so the eight warps of a CTA
 // run at the pace of their slowest detection (~20 % of the warp time was spent waiting for the next tile).  Here no
@@ -16,10 +16,16 @@
 //   * rows that repeat the previous row of their image (FilterDetections' -1 padding) are skipped when claimed; the
 //     warp that finishes a detection also writes its results to the identical rows that follow it.  One launch per
 //     call, no work lists, no memset: the counters are reset by the last warp / CTA that uses them.
-// The per-hypothesis arithmetic, the VERIFIED filter and the exact bookkeeping are those of gpp_poll2.cuh
-// (fit_road_planes.py:86-119); only the schedule and the data movement differ.
+// Modes: FAST and VERIFIED scan the pair-interleaved database with the packed arithmetic of gpp_poll2.cuh; EXACT
+// (fp32) and F64 scan the plain database with the scalar hypothesis of gpp_math.cuh, one plane per lane, straight from
+// L2 (they are bound by their own arithmetic: 155 / 300 instructions per 16 / 32 bytes).  The epilogue can run the two
+// steps that follow polling in the reference's driver -- pose recovery and the KITTI record (gpp_pose.cuh) -- on the
+// winner it has just recomputed.
 #pragma once
+#include <type_traits>
+
 #include "gpp_poll2.cuh"
+#include "gpp_pose.cuh"
 
 #ifndef GPP_STAGE2
 #define GPP_STAGE2 1      /* 0: experiment -- stage-1 survivors of the all-six phase go straight to the exact queue */
@@ -27,21 +33,27 @@
 
 namespace gpp {
 
-struct SegPartial {       // result of one plane segment of a detection
-    float r;
-    int M, idx, pad;
+struct SegPartial {       // result of one plane segment of a detection (16 bytes)
+    double r;
+    int M, idx;
 };
+
+enum { kModeFast = 0, kModeVerified = 1, kModeExact = 2, kModeF64 = 3 };
 
 struct PollArgs3 {
     const float *boxes, *dims, *pinv;
     const int32_t *orient;
-    const u64 *pairs;            // pair-interleaved normalised DB (see PollArgs2)
-    const float4 *planes;        // plain normalised DB, for the exact paths
+    const u64 *pairs;            // pair-interleaved normalised fp32 DB (see PollArgs2): FAST / VERIFIED scans
+    const float4 *planes;        // plain normalised fp32 DB: exact paths, EXACT scan
+    const double4 *planes64;     // fp64 DB: F64 scan
     int n_planes, n_pairs_padded, dets_per_image;
     long long n_det;
-    float *keypoints, *keyplanes, *residuals;
+    void *keypoints, *keyplanes, *residuals;     // float, or double in the F64 mode
     long long *best;
+    // optional fused steps after polling (run_network.py:137-247, :297-327); nullptr = off.  pose_kitti needs the others.
+    float *pose_locations, *pose_angles, *pose_dimensions, *pose_kitti;
     // schedule
+    int det_stride;              // 1; n > 1 polls rows 0, n, 2n, ... only (runtime audit), without the repeated-row logic
     int resident_rows;           // rows of `pairs` kept in shared memory (0 = stream everything from L2)
     int n_seg, rows_per_seg;     // plane segments per detection
     unsigned long long *claim;   // [0] work-item counter, [1] CTAs that have left; zero at launch, reset by the last CTA
@@ -468,20 +480,85 @@ __host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
     return size_t(resident_rows) * 1024 + size_t(warps) * kWarpSmem3 + 16;
 }
 
-// kSeg: detections are cut into plane segments (small batches); the large-batch instantiation carries none of it
-template <int kWarps, int kVMode, bool kSeg>
+// ------------------------------------------------------------------ EXACT / F64: scalar scan, one plane per lane
+// The hypothesis comes in two halves (gpp_math.cuh): once a plane with six votes is known, a plane matters only if its
+// residual sum does not exceed the warp's best six-vote residual; the sum of the three bottom-face residuals never
+// exceeds the full sum (rounded addition of non-negative terms is monotone; a NaN / inf sum never wins), so
+// (r1 + r2) + r3 > best for all 32 lanes ends the hypothesis after its first half -- X_t, one division and three
+// square roots are skipped for about three of four rows, and nothing that is kept changes by a bit.
+template <class P>
+__device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typename P::T4 *__restrict__ planes,
+                                            const int p_begin, const int p_end, const int lane, const bool same_rays,
+                                            LaneState<typename P::T> &st) {
+    typedef typename P::T T;
+    typedef typename P::T4 T4;
+    const T highest = P::highest();
+    st.reset(highest);
+    if (same_rays) {
+        // FilterDetections' padding rows: the cheap form that identical rays allow (bit-identical, gpp_math.cuh)
+#pragma unroll 2
+        for (int j = p_begin + lane; j < p_end; j += 32) {
+            const T4 pl = planes[j];
+            T X[4][3];
+            int V; T R; bool z;
+            hypothesis_same_rays<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
+            st.update(V, R, z, j, highest);
+        }
+        return;
+    }
+    bool m6 = false;
+    T wbest = highest;
+    int it = 0;
+#pragma unroll 1
+    for (int j0 = p_begin; j0 < p_end; j0 += 32, ++it) {
+        const int j = j0 + lane;
+        const bool valid = j < p_end;                      // lanes past the end poll the last plane again and drop it
+        const T4 pl = planes[valid ? j : p_end - 1];
+        T X[4][3];
+        int V; T R; bool zneg;
+        if (m6) {
+            T rb[3];
+            hypothesis_bottom<P>(det, pl.x, pl.y, pl.z, pl.w, X, rb, zneg);
+            const T S3 = P::add(P::add(rb[0], rb[1]), rb[2]);
+            if (!__any_sync(0xffffffffu, valid && !(S3 > wbest))) continue;
+            hypothesis_top<P>(det, pl.x, pl.y, pl.z, X, rb, V, R);
+            if (valid) st.update(V, R, zneg, j, highest);
+            wbest = warp_min_value(st.M == 6 ? st.bestR : highest);
+        } else {
+            hypothesis<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            if (valid) st.update(V, R, zneg, j, highest);
+            if ((it & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
+                m6 = true;
+                wbest = warp_min_value(st.M == 6 ? st.bestR : highest);
+            }
+        }
+    }
+}
+
+template <int kMode> struct ModePolicy { typedef ExactF32 type; };
+template <> struct ModePolicy<kModeF64> { typedef ExactF64 type; };
+
+// kSeg: detections are cut into plane segments (small batches); the large-batch instantiation carries none of it.
+// kPose: the epilogue also runs pose recovery and the KITTI record (their double-precision code and stack frame stay
+// out of the plain instantiations).
+template <int kWarps, int kMode, bool kSeg, bool kPose>
 __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 args) {
-    constexpr bool kVerified = kVMode != 0;
+    constexpr bool kVerified = kMode == kModeVerified;
+    constexpr bool kPacked = kMode == kModeFast || kMode == kModeVerified;
+    typedef typename ModePolicy<kMode>::type P;       // the exact policy of the output type
+    typedef typename P::T T;
+    typedef typename P::T4 T4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int N = args.n_planes;
-    const int NR = args.n_pairs_padded >> 5;                  // rows of 32 pairs
-    const int res = args.resident_rows;
+    const int NR = args.n_pairs_padded >> 5;                  // rows of 32 pairs = 64 planes
+    const int res = kPacked ? args.resident_rows : 0;
     unsigned char *warp_area = smem_raw + size_t(res) * 1024 + size_t(warp) * kWarpSmem3;
     int *queue = reinterpret_cast<int *>(warp_area);
     float *detx = reinterpret_cast<float *>(warp_area + kVerifyQueue * sizeof(int));
     uint64_t *stage_bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(res) * 1024 + size_t(kWarps) * kWarpSmem3);
+    const T4 *planesT = kMode == kModeF64 ? reinterpret_cast<const T4 *>(args.planes64) : reinterpret_cast<const T4 *>(args.planes);
 
     // ---- stage the resident rows: 1-D TMA bulk copies, one mbarrier for the lot
     if (res > 0) {
@@ -500,7 +577,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
     }
 
     const int n_seg = kSeg ? args.n_seg : 1;
-    const unsigned long long n_items = (unsigned long long)args.n_det * (unsigned)n_seg;
+    const int stride = args.det_stride;
+    const unsigned long long n_rows = (unsigned long long)((args.n_det + stride - 1) / stride);
+    const unsigned long long n_items = n_rows * (unsigned)n_seg;
     unsigned long long next_claim = 0;
     if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);
     next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
@@ -510,30 +589,31 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
         if (item >= n_items) break;                                  // warp-uniform: this warp retires
         if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);     // claimed one item ahead
         next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
-        const long long m = kSeg ? (long long)(item / (unsigned)n_seg) : (long long)item;
-        const int seg = kSeg ? int(item - (unsigned long long)m * (unsigned)n_seg) : 0;
+        const long long slot = kSeg ? (long long)(item / (unsigned)n_seg) : (long long)item;   // index into the scratch
+        const int seg = kSeg ? int(item - (unsigned long long)slot * (unsigned)n_seg) : 0;
+        const long long m = slot * stride;
         // a row that repeats the previous row of its image is written by the warp that polls that row
-        if ((m % args.dets_per_image) != 0 && same_detection(args, m, m - 1, lane)) continue;
+        if (stride == 1 && (m % args.dets_per_image) != 0 && same_detection(args, m, m - 1, lane)) continue;
 
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
+        Detection<P> detE;
+        load_detection<P, P>(detE, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
+                             args.pinv + 12 * (m / args.dets_per_image));
+        const bool same_rays = same_ground_rays(detE);
         DetConst D;
-        bool same_rays;
-        {
-            Detection<ExactF32> det0;
-            load_detection<ExactF32, ExactF32>(det0, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
-                                               args.pinv + 12 * (m / args.dets_per_image));
+        if constexpr (kPacked) {
+            // the exact constants are only needed by the rare exact paths and the epilogue: parked in shared memory
 #pragma unroll
-            for (int i = 0; i < 6; ++i) D.td[i] = det0.td[i];
-            fast_constants(D, det0);
-            same_rays = kVerified && same_ground_rays(det0);
+            for (int i = 0; i < 6; ++i) D.td[i] = detE.td[i];
+            fast_constants(D, detE);
             __syncwarp();                            // the previous item's readers are done
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    detx[i] = det0.dl[i]; detx[3 + i] = det0.dm[i]; detx[6 + i] = det0.dr[i]; detx[9 + i] = det0.dt[i];
+                    detx[i] = detE.dl[i]; detx[3 + i] = detE.dm[i]; detx[6 + i] = detE.dr[i]; detx[9 + i] = detE.dt[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 6; ++i) detx[12 + i] = det0.td[i];
+                for (int i = 0; i < 6; ++i) detx[12 + i] = detE.td[i];
                 store_cold(detx, D);
             }
             __syncwarp();
@@ -541,56 +621,51 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
 
         const int r_begin = kSeg ? seg * args.rows_per_seg : 0;
         const int r_end = kSeg ? min(NR, r_begin + args.rows_per_seg) : NR;
-        RowSource src;
-        src.init(smem_u32(smem_raw), args.pairs, res, r_begin, r_end, lane);
-        ulonglong2 c0, c1;
-        src.load_again(c0, c1);
         int Mw, idx;
-        float rbest;
-        if (kVerified && same_rays) {
-            // FilterDetections' padding row: all its hypotheses are within rounding noise of each other, so the filter
-            // cannot drop any -- every plane of the segment in the exact arithmetic right away, in the cheap form that
-            // identical rays allow (gpp_math.cuh)
-            const Detection<ExactF32> det = load_det_exact(detx);
-            LaneState<float> st;
-            st.reset(FLT_MAX);
-            const int p_end = min(N, r_end << 6);
-#pragma unroll 2
-            for (int j = (r_begin << 6) + lane; j < p_end; j += 32) {
-                const float4 pl = __ldg(args.planes + j);
-                float X[4][3];
-                int V; float R; bool z;
-                hypothesis_same_rays<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
-                st.update(V, R, z, j, FLT_MAX);
-            }
+        T rbest;
+        if (!kPacked || (kVerified && same_rays)) {
+            // EXACT / F64, and VERIFIED on FilterDetections' padding rows (all their hypotheses are within rounding
+            // noise of each other, so the filter cannot drop any): every plane of the segment in the exact arithmetic
+            Detection<P> det;
+            if constexpr (kPacked) det = load_det_exact(detx); else det = detE;
+            LaneState<T> st;
+            scalar_scan<P>(det, planesT, r_begin << 6, min(N, r_end << 6), lane, same_rays, st);
             Mw = __reduce_max_sync(0xffffffffu, st.M);
-            rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
+            rbest = (st.M == Mw) ? st.bestR : P::highest();
             idx = st.bestIdx;
 #ifdef GPP_STATS
-            if (lane == 0) { atomicAdd(&g_stats3[5], 1ull); atomicAdd(&g_stats3[6], 1ull); }
+            if (kVerified && lane == 0) { atomicAdd(&g_stats3[5], 1ull); atomicAdd(&g_stats3[6], 1ull); }
 #endif
-        } else if (kVerified) {
-            VerifiedScan sc;
-            sc.begin();
-            for (; src.rows_left > 0; src.advance()) {
-                // segments of one detection share their bounds: the key is fetched here and used after the row
-                const bool share = kSeg && (src.rows_left & 3) == 0;
-                unsigned long long key = 0ull;
-                if (share) key = *reinterpret_cast<volatile unsigned long long *>(args.seg_best + m);
-                const int Mb = sc.Mcur;
-                const float wb = sc.wbest;
-                sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
-                if (kSeg && (sc.Mcur != Mb || sc.wbest < wb) && lane == 0)
-                    atomicMax(args.seg_best + m, seg_key(sc.Mcur, sc.wbest));
-                if (share) sc.adopt(key, detx);
+        } else if constexpr (kPacked) {
+            RowSource src;
+            src.init(smem_u32(smem_raw), args.pairs, res, r_begin, r_end, lane);
+            ulonglong2 c0, c1;
+            src.load_again(c0, c1);
+            float rb;
+            if (kVerified) {
+                VerifiedScan sc;
+                sc.begin();
+                for (; src.rows_left > 0; src.advance()) {
+                    // segments of one detection share their bounds: the key is fetched here and used after the row
+                    const bool share = kSeg && (src.rows_left & 3) == 0;
+                    unsigned long long key = 0ull;
+                    if (share) key = *reinterpret_cast<volatile unsigned long long *>(args.seg_best + slot);
+                    const int Mb = sc.Mcur;
+                    const float wb = sc.wbest;
+                    sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
+                    if (kSeg && (sc.Mcur != Mb || sc.wbest < wb) && lane == 0)
+                        atomicMax(args.seg_best + slot, seg_key(sc.Mcur, sc.wbest));
+                    if (share) sc.adopt(key, detx);
+                }
+                sc.finish(detx, args.planes, queue, lane);
+                sc.result(Mw, rb, idx);
+            } else {
+                FastScan sc;
+                sc.begin();
+                for (; src.rows_left > 0; src.advance()) sc.row(D, src, c0, c1);
+                sc.result(Mw, rb, idx);
             }
-            sc.finish(detx, args.planes, queue, lane);
-            sc.result(Mw, rbest, idx);
-        } else {
-            FastScan sc;
-            sc.begin();
-            for (; src.rows_left > 0; src.advance()) sc.row(D, src, c0, c1);
-            sc.result(Mw, rbest, idx);
+            rbest = rb;
         }
         rbest = warp_min_first(rbest, idx);
 
@@ -598,83 +673,89 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             // ---- hand the partial result in; the warp that completes the detection merges and continues
             unsigned arrived = 0;
             if (lane == 0) {
-                SegPartial p;
-                p.r = rbest; p.M = Mw; p.idx = idx; p.pad = 0;
-                __stcg(reinterpret_cast<int4 *>(args.partials + m * n_seg + seg),
-                       make_int4(__float_as_int(p.r), p.M, p.idx, 0));
+                __stcg(reinterpret_cast<int4 *>(args.partials + slot * n_seg + seg),
+                       make_int4(__double2loint((double)rbest), __double2hiint((double)rbest), Mw, idx));
                 __threadfence();
-                arrived = atomicAdd(args.seg_arrived + m, 1u);
+                arrived = atomicAdd(args.seg_arrived + slot, 1u);
             }
             arrived = __shfl_sync(0xffffffffu, arrived, 0);
             if (arrived != unsigned(n_seg - 1)) continue;
             __threadfence();
-            SegPartial p;
-            p.M = -1; p.r = FLT_MAX; p.idx = 0;
+            int pM = -1, pidx = 0;
+            T pr = P::highest();
             if (lane < n_seg) {
-                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(args.partials + m * n_seg + lane));
-                p.r = __int_as_float(raw.x); p.M = raw.y; p.idx = raw.z;
+                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(args.partials + slot * n_seg + lane));
+                pr = (T)__hiloint2double(raw.y, raw.x); pM = raw.z; pidx = raw.w;
             }
-            Mw = __reduce_max_sync(0xffffffffu, p.M);
-            rbest = (p.M == Mw) ? p.r : FLT_MAX;
-            idx = p.idx;
+            Mw = __reduce_max_sync(0xffffffffu, pM);
+            rbest = (pM == Mw) ? pr : P::highest();
+            idx = pidx;
             rbest = warp_min_first(rbest, idx);
             if (lane == 0) {                          // leave the scratch as it was found
-                args.seg_arrived[m] = 0u;
-                args.seg_best[m] = 0ull;
+                args.seg_arrived[slot] = 0u;
+                args.seg_best[slot] = 0ull;
             }
         }
 
         // ---- epilogue: lazy first-masked search, exact recompute of the winner (fit_road_planes.py:116-137)
-        const Detection<ExactF32> det = load_det_exact(detx);
-        const bool have_cand = rbest < FLT_MAX;
+        Detection<P> det;
+        if constexpr (kPacked) det = load_det_exact(detx); else det = detE;
+        const bool have_cand = rbest < P::highest();
         bool sentinel = false;
-        if (!(rbest < 100.0f)) {
+        if (!(rbest < T(100))) {
+            // the constant 100 carried by masked planes may win: find the first masked plane
             int first_masked = -1;
-            for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
-                const int p = p0 + lane;                         // pair index; the padded DB covers it
-                const ulonglong2 v0 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p);
-                const ulonglong2 v1 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p + 1);
-                int V0, V1;
-                bool z0, z1;
-                if (kVerified) {
-                    const f2 a01 = from_u64(v0.x), b01 = from_u64(v0.y), c01 = from_u64(v1.x), d01 = from_u64(v1.y);
-                    float Rx;
-                    exact_one(det, lo(a01), lo(b01), lo(c01), lo(d01), V0, Rx, z0);
-                    exact_one(det, hi(a01), hi(b01), hi(c01), hi(d01), V1, Rx, z1);
-                } else {
+            if constexpr (kMode == kModeFast) {
+                for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
+                    const int p = p0 + lane;                         // pair index; the padded DB covers it
+                    const ulonglong2 v0 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p);
+                    const ulonglong2 v1 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p + 1);
                     PairResult h;
                     eval_pair<false>(PackFast(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
-                    V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
-                    V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-                    z0 = lo(h.zc) < 0.0f;
-                    z1 = hi(h.zc) < 0.0f;
+                    const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
+                    const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
+                    const bool mk0 = (2 * p < N) && ((V0 < Mw) || lo(h.zc) < 0.0f);
+                    const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || hi(h.zc) < 0.0f);
+                    const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
+                    if (b0 | b1) {
+                        const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
+                        const int f1 = b1 ? 2 * (p0 + __ffs(b1) - 1) + 1 : 0x7fffffff;
+                        first_masked = min(f0, f1);
+                    }
                 }
-                const bool mk0 = (2 * p < N) && ((V0 < Mw) || z0);
-                const bool mk1 = (2 * p + 1 < N) && ((V1 < Mw) || z1);
-                const unsigned b0 = __ballot_sync(0xffffffffu, mk0), b1 = __ballot_sync(0xffffffffu, mk1);
-                if (b0 | b1) {
-                    const int f0 = b0 ? 2 * (p0 + __ffs(b0) - 1) : 0x7fffffff;
-                    const int f1 = b1 ? 2 * (p0 + __ffs(b1) - 1) + 1 : 0x7fffffff;
-                    first_masked = min(f0, f1);
+            } else {
+                for (int j0 = 0; j0 < N && first_masked < 0; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool masked = false;
+                    if (j < N) {
+                        const T4 pl = planesT[j];
+                        T X[4][3];
+                        int V; T R; bool zneg;
+                        hypothesis<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+                        masked = (V < Mw) || zneg;
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, masked);
+                    if (b) first_masked = j0 + __ffs(b) - 1;
                 }
             }
             if (first_masked >= 0) {
-                if (!have_cand || 100.0f < rbest || (100.0f == rbest && first_masked < idx)) {
+                if (!have_cand || T(100) < rbest || (T(100) == rbest && first_masked < idx)) {
                     sentinel = true;
                     idx = first_masked;
                 }
             } else if (!have_cand) {
-                idx = 0;
+                idx = 0;                                      // nothing compares below `highest`
             }
         }
         // the winner in the exact arithmetic (every lane computes the same values; lane k keeps output word k)
-        float word = 0.0f;
+        T word = T(0);
+        float pword = 0.0f;
         {
-            const float4 pl = __ldg(args.planes + idx);
-            float X[4][3];
-            int V; float R; bool zneg;
-            hypothesis<ExactF32>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
-            const float rr = __fdiv_rn(sentinel ? 100.0f : R, 6.0f);
+            const T4 pl = planesT[idx];
+            T X[4][3];
+            int V; T R; bool zneg;
+            hypothesis<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            const T rr = P::div(sentinel ? T(100) : R, T(6));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -684,34 +765,62 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             word = (lane == 14) ? pl.z : word;
             word = (lane == 15) ? pl.w : word;
             word = (lane == 16) ? rr : word;
-            // this row and the identical rows that follow it in the image (their claims were skipped).  The length of
-            // the run is found 32 rows at a time -- lane i compares row m + 1 + i with its predecessor -- so that a
-            // padded image costs a few load latencies, not one per padding row.
-            const long long image_end = (m / args.dets_per_image + 1) * (long long)args.dets_per_image;
-            long long run_end = m + 1;
-            for (long long base = m + 1; base < image_end; base += 32) {
-                const long long n = base + lane;
-                bool same = n < image_end;
-                if (same) {
-                    const unsigned *bx = reinterpret_cast<const unsigned *>(args.boxes) + 12 * n;
-                    const unsigned *dm = reinterpret_cast<const unsigned *>(args.dims) + 3 * n;
-                    unsigned diff = (unsigned)(__ldg(args.orient + n) ^ __ldg(args.orient + n - 1));
+            if constexpr (kPose) {
+                // the two steps after polling (run_network.py:137-247, :297-327) on the key-points just computed; rows
+                // whose orientation is no class (padding) keep zeros and their dimensions, like the stand-alone entries
+                float kp[12], pose9[9], rec[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) diff |= __ldg(bx + i) ^ __ldg(bx + i - 12);     // all loads in flight at once
+                for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) diff |= __ldg(dm + i) ^ __ldg(dm + i - 3);
-                    same = diff == 0u;
-                }
-                const unsigned b = __ballot_sync(0xffffffffu, same);
-                const int lead = __ffs(~b) - 1;                   // rows of this batch that continue the run (-1: all 32)
-                run_end = base + (lead < 0 ? 32 : lead);
-                if (lead >= 0) break;
+                    for (int i = 0; i < 3; ++i) kp[3 * k + i] = (float)X[k][i];
+                const int o = __ldg(args.orient + m);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) pose9[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pose9[6 + i] = __ldg(args.dims + 3 * m + i);
+                if (o >= 0 && o <= 3) pose_from_keypoints(kp, pose9[7], o, pose9);
+                if (args.pose_kitti) kitti_record(pose9, rec);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) pword = (lane == i) ? pose9[i] : pword;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pword = (lane == 9 + i) ? rec[i] : pword;
             }
-            for (long long n = m; n < run_end; ++n) {
-                if (lane < 12) args.keypoints[12 * n + lane] = word;
-                else if (lane < 16) args.keyplanes[4 * n + (lane - 12)] = word;
-                else if (lane == 16) args.residuals[n] = word;
-                else if (lane == 17 && args.best) args.best[n] = idx;
+        }
+        // this row and the identical rows that follow it in the image (their claims were skipped).  The length of
+        // the run is found 32 rows at a time -- lane i compares row m + 1 + i with its predecessor -- so that a
+        // padded image costs a few load latencies, not one per padding row.
+        const long long image_end = (m / args.dets_per_image + 1) * (long long)args.dets_per_image;
+        long long run_end = m + 1;
+        for (long long base = m + 1; stride == 1 && base < image_end; base += 32) {
+            const long long n = base + lane;
+            bool same = n < image_end;
+            if (same) {
+                const unsigned *bx = reinterpret_cast<const unsigned *>(args.boxes) + 12 * n;
+                const unsigned *dm = reinterpret_cast<const unsigned *>(args.dims) + 3 * n;
+                unsigned diff = (unsigned)(__ldg(args.orient + n) ^ __ldg(args.orient + n - 1));
+#pragma unroll
+                for (int i = 0; i < 12; ++i) diff |= __ldg(bx + i) ^ __ldg(bx + i - 12);     // all loads in flight at once
+#pragma unroll
+                for (int i = 0; i < 3; ++i) diff |= __ldg(dm + i) ^ __ldg(dm + i - 3);
+                same = diff == 0u;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, same);
+            const int lead = __ffs(~b) - 1;                   // rows of this batch that continue the run (-1: all 32)
+            run_end = base + (lead < 0 ? 32 : lead);
+            if (lead >= 0) break;
+        }
+        T *kp_out = static_cast<T *>(args.keypoints), *kpl_out = static_cast<T *>(args.keyplanes);
+        T *res_out = static_cast<T *>(args.residuals);
+        for (long long n = m; n < run_end; ++n) {
+            if (lane < 12) kp_out[12 * n + lane] = word;
+            else if (lane < 16) kpl_out[4 * n + (lane - 12)] = word;
+            else if (lane == 16) res_out[n] = word;
+            else if (lane == 17 && args.best) args.best[n] = idx;
+            if constexpr (kPose) {
+                if (lane < 3) args.pose_locations[3 * n + lane] = pword;
+                else if (lane < 6) args.pose_angles[3 * n + (lane - 3)] = pword;
+                else if (lane < 9) args.pose_dimensions[3 * n + (lane - 6)] = pword;
+                else if (lane < 13 && args.pose_kitti) args.pose_kitti[4 * n + (lane - 9)] = pword;
             }
         }
     }

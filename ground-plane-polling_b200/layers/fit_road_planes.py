@@ -81,9 +81,12 @@ class PlanePoller(object):
         return out
 
     # ------------------------------------------------------------------ numpy entry
-    def fit(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False, out=None):
+    def fit(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False, out=None, return_pose=False,
+            return_kitti=False):
         """fit_road_planes against the resident database.  Returns [keypoints (B, D, 4, 3),
-        keyplanes (B, D, 1, 4), residuals (B, D)] float32 (float64 in mode 'f64') [+ best index int64].
+        keyplanes (B, D, 1, 4), residuals (B, D)] float32 (float64 in mode 'f64') [+ best index int64]
+        [+ locations, angles, dimensions (B, D, 3) with ``return_pose``] [+ KITTI records (B, D, 4) with ``return_kitti``:
+        both computed in the polling kernel's epilogue, one launch for everything].
         ``out`` may hold preallocated C-contiguous result arrays (e.g. pinned host memory) to write into."""
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in _lib.MODES:
@@ -117,7 +120,19 @@ class PlanePoller(object):
             keyplanes = np.empty((B, D, 1, 4), out_t)
             residuals = np.empty((B, D), out_t)
             best = np.empty((B, D), np.int64) if return_index else None
-        if mode == 'f64':
+        pose = None
+        if return_pose or return_kitti:
+            if mode == 'f64':
+                raise ValueError("return_pose / return_kitti are computed in float32 like the reference's driver: "
+                                 "not available in mode 'f64'")
+            pose = [np.empty((B, D, 3), np.float32) for _ in range(3)] + \
+                   ([np.empty((B, D, 4), np.float32)] if return_kitti else [None])
+            rc = self._lib.gpp_fit_pose_host(self._h, _lib.ptr(boxes), _lib.ptr(dimensions), _lib.ptr(orientations),
+                                             _lib.ptr(P_inv), B, D, _lib.ptr(keypoints), _lib.ptr(keyplanes),
+                                             _lib.ptr(residuals), _lib.ptr(best), _lib.ptr(pose[0]), _lib.ptr(pose[1]),
+                                             _lib.ptr(pose[2]), _lib.ptr(pose[3]), _lib.MODES[mode])
+            _lib.check(rc, 'gpp_fit_pose_host')
+        elif mode == 'f64':
             rc = self._lib.gpp_fit_host_f64(self._h, _lib.ptr(boxes), _lib.ptr(dimensions), _lib.ptr(orientations),
                                             _lib.ptr(P_inv), B, D, _lib.ptr(keypoints), _lib.ptr(keyplanes),
                                             _lib.ptr(residuals), _lib.ptr(best))
@@ -130,6 +145,10 @@ class PlanePoller(object):
         out = [keypoints, keyplanes, residuals]
         if return_index:
             out.append(best)
+        if return_pose:
+            out += pose[:3]
+        if return_kitti:
+            out.append(pose[3])
         return out
 
     # ------------------------------------------------------------------ torch (device tensor) entry
@@ -150,9 +169,10 @@ class PlanePoller(object):
                                                    ctypes.c_void_p(stream)), 'gpp_set_planes_device')
         self._dev_planes = (planes, planes._version)
 
-    def fit_torch(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False):
+    def fit_torch(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False, return_pose=False,
+                  return_kitti=False):
         """Device-resident call: CUDA tensors in, CUDA tensors out, enqueued on torch's current stream,
-        no host synchronisation."""
+        no host synchronisation.  ``return_pose`` / ``return_kitti`` as in ``fit``."""
         import torch
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in _lib.MODES:
@@ -180,8 +200,19 @@ class PlanePoller(object):
         best = torch.empty((B, D), dtype=torch.int64, device=dev) if return_index else None
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() else None  # noqa: E731
-        if B * D > 0:
+        pose = None
+        if return_pose or return_kitti:
             if mode == 'f64':
+                raise ValueError("return_pose / return_kitti are not available in mode 'f64'")
+            pose = [torch.empty((B, D, 3), dtype=torch.float32, device=dev) for _ in range(3)] + \
+                   ([torch.empty((B, D, 4), dtype=torch.float32, device=dev)] if return_kitti else [None])
+        if B * D > 0:
+            if pose is not None:
+                rc = self._lib.gpp_fit_pose_device(self._h, vp(boxes), vp(dimensions), vp(orientations), vp(P_inv), B, D,
+                                                   vp(keypoints), vp(keyplanes), vp(residuals), vp(best), vp(pose[0]),
+                                                   vp(pose[1]), vp(pose[2]), vp(pose[3]), _lib.MODES[mode], stream)
+                _lib.check(rc, 'gpp_fit_pose_device')
+            elif mode == 'f64':
                 rc = self._lib.gpp_fit_device_f64(self._h, vp(boxes), vp(dimensions), vp(orientations), vp(P_inv),
                                                   B, D, vp(keypoints), vp(keyplanes), vp(residuals), vp(best),
                                                   stream)
@@ -194,6 +225,10 @@ class PlanePoller(object):
         out = [keypoints, keyplanes, residuals]
         if return_index:
             out.append(best)
+        if return_pose:
+            out += pose[:3]
+        if return_kitti:
+            out.append(pose[3])
         return out
 
     # ------------------------------------------------------------------ measurement helpers
@@ -226,10 +261,6 @@ class PlanePoller(object):
             # + what the VERIFIED filters test: votes possible within the margin, z-check passable within it
             return votes & 15, resid, (zneg & 1).astype(bool), margin, votes >> 4, (zneg & 2).astype(bool)
         return votes & 15, resid, (zneg & 1).astype(bool)
-
-    def debug_set_config(self, variant=0, ctas_per_sm=0):
-        _lib.check(self._lib.gpp_debug_set_config(self._h, int(variant), int(ctas_per_sm)),
-                   'gpp_debug_set_config')
 
     def debug_set_schedule(self, n_seg=0, resident_rows=-1):
         """Test / tuning hook of the resident-database kernel: plane segments per detection (0 = automatic) and rows
@@ -297,7 +328,7 @@ def _plane_groups(planes, B):
 
 
 def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False, device=None,
-                    out=None, return_pose=False):
+                    out=None, return_pose=False, return_kitti=False):
     """ Identify 3D keypoints and keyplane for each detection (drop-in for fit_road_planes.py:49).
     Args
         boxes                 : (num_batch, num_dets, 12) boxes in (x1, y1, x2, y2, xl, yl, xm, ym, xr, yr, xt, yt) format.
@@ -314,16 +345,9 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     ``return_index`` appends the winning plane index (int64), ``device`` picks the GPU, ``out`` is a list of
     preallocated result arrays (single shared database only), ``return_pose`` appends ``locations (B, D, 3)``,
     ``angles (B, D, 3)`` (Rodrigues vector) and the corrected ``dimensions (B, D, 3)`` of EVERY row as the driver
-    computes them for the rows it keeps (bin/run_network.py:137-247, ``recover_pose``).
+    computes them for the rows it keeps (bin/run_network.py:137-247), ``return_kitti`` appends the KITTI writer's
+    ``(alpha, h, Y, r_y)`` rows ``(B, D, 4)`` (:297-327) -- both run in the polling kernel's epilogue (one launch).
     """
-    if return_pose:
-        res = fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=mode, return_index=return_index,
-                              device=device, out=out)
-        from ..utils.pose import recover_pose
-        shape = res[2].shape
-        loc, ang, dim = recover_pose(res[0].reshape(-1, 12), np.asarray(dimensions).reshape(-1, 3),
-                                     np.asarray(orientations).reshape(-1), device=device)
-        return list(res) + [loc.reshape(shape + (3,)), ang.reshape(shape + (3,)), dim.reshape(shape + (3,))]
     poller = get_poller(device)
     boxes = np.asarray(boxes)
     if boxes.ndim != 3:
@@ -332,7 +356,8 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     groups = _plane_groups(planes, B)
     if len(groups) == 1:
         poller.set_planes(groups[0][2])
-        return poller.fit(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index, out=out)
+        return poller.fit(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index, out=out,
+                          return_pose=return_pose, return_kitti=return_kitti)
     if out is not None:
         raise ValueError('out= is only supported with one plane database shared by the batch')
     dimensions, orientations, P_inv = np.asarray(dimensions), np.asarray(orientations), np.asarray(P_inv)
@@ -340,23 +365,17 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     for b0, b1, db in groups:
         poller.set_planes(db)
         parts.append(poller.fit(boxes[b0:b1], dimensions[b0:b1], orientations[b0:b1], P_inv[b0:b1], mode=mode,
-                                return_index=return_index))
+                                return_index=return_index, return_pose=return_pose, return_kitti=return_kitti))
     return [np.concatenate([p[i] for p in parts], axis=0) for i in range(len(parts[0]))]
 
 
 def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False,
-                          return_pose=False):
+                          return_pose=False, return_kitti=False):
     """Same operator on CUDA tensors (zero-copy, torch's current stream, no host sync).  ``planes`` is one
     (N, 4) / (1, N, 4) database shared by the batch (torch tensor on any device, or numpy).  ``return_pose`` appends
-    locations, angles and corrected dimensions, (B, D, 3) each, computed on the device right behind the polling."""
+    locations, angles and corrected dimensions, (B, D, 3) each, ``return_kitti`` the (B, D, 4) KITTI records -- computed in
+    the polling kernel's epilogue."""
     import torch
-    if return_pose:
-        res = fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=mode,
-                                    return_index=return_index)
-        from ..utils.pose import recover_pose_torch
-        shape = tuple(res[2].shape)
-        loc, ang, dim = recover_pose_torch(res[0].to(torch.float32), dimensions, orientations)
-        return list(res) + [loc.view(shape + (3,)), ang.view(shape + (3,)), dim.view(shape + (3,))]
     poller = get_poller(boxes.device.index if boxes.device.index is not None else torch.cuda.current_device())
     if isinstance(planes, torch.Tensor):
         if planes.dim() == 3:
@@ -372,7 +391,8 @@ def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=N
         if len(groups) != 1:
             raise ValueError('fit_road_planes_torch takes one database per call')
         poller.set_planes(groups[0][2])
-    return poller.fit_torch(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index)
+    return poller.fit_torch(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index,
+                            return_pose=return_pose, return_kitti=return_kitti)
 
 
 def fit_road_planes_dlpack(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False):

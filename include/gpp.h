@@ -113,6 +113,22 @@ int gpp_fit_device(gpp_handle *h, const float *boxes, const float *dimensions, c
                    const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
                    int64_t *best_index, int mode, void *stream);
 
+/* fit_road_planes + the two steps that follow it in the reference's driver, in ONE kernel launch: the polling kernel's
+ * epilogue runs pose recovery (run_network.py:137-247) and, if `kitti` is not NULL, the KITTI record arithmetic
+ * (:297-327) on the winner it has just recomputed -- no second launch, no round trip of the key-points.
+ *   locations, angles, dimensions_out   B*D*3 floats out each (as gpp_pose_*: rows whose orientation is no class in
+ *                                       0..3 get zeros and their input dimensions)
+ *   kitti                               B*D*4 floats out (alpha, h, Y, r_y) or NULL
+ * The results equal gpp_fit_* followed by gpp_pose_* / gpp_kitti_* bit for bit (same device functions). */
+int gpp_fit_pose_host(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                      const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                      int64_t *best_index, float *locations, float *angles, float *dimensions_out, float *kitti,
+                      int mode);
+int gpp_fit_pose_device(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
+                        const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                        int64_t *best_index, float *locations, float *angles, float *dimensions_out, float *kitti,
+                        int mode, void *stream);
+
 /* FP64 verify mode: same inputs (float32, promoted exactly), search and outputs in double. */
 int gpp_fit_host_f64(gpp_handle *h, const float *boxes, const float *dimensions, const int32_t *orientations,
                      const float *P_inv, int B, int D, double *keypoints, double *keyplanes,

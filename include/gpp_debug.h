@@ -23,13 +23,6 @@ extern "C" {
  * repetition, and operations per SM clock (from clock64 inside the kernel).  Any out pointer may be NULL. */
 int gpp_microbench(gpp_handle *h, int kind, double *ops_per_s, float *ms, double *ops_per_clk_sm);
 
-/* Tuning / test hook: `variant` selects the batch kernel of the packed fp32 modes (0 = built-in default).
- * FAST: 2 / 3 / 4 = the kernel compiled for that many resident CTAs per SM (register budget 128 / 80 / 64).
- * VERIFIED: 2 / 3 = group-synchronous kernel with 2 / 3 CTAs per SM, 4 = per-warp claiming with a rotated scan
- * (the default).  +100 forces, +200 forbids the small-batch kernels (one detection per CTA, planes split over the
- * warps; default: automatic by batch size); `ctas_per_sm` sizes the persistent grid (0 = occupancy maximum). */
-int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
-
 /* Test hook: the per-hypothesis scores of ONE detection against the resident database, computed by the same
  * device functions the search loops call -- `which` 0 = EXACT arithmetic, 1 = FAST (general path), 2 = FAST
  * (all-six-votes path, merged reciprocal), 3 = stage 1 of the VERIFIED all-six path (resid = sum of the three
@@ -39,9 +32,9 @@ int gpp_debug_set_config(gpp_handle *h, int variant, int ctas_per_sm);
 int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int orientation, const float *pinv12,
                      int which, int32_t *votes, float *resid, int32_t *zneg, float *margin);
 
-/* Schedule of the resident-database kernel (default kernel of the FAST / VERIFIED modes, csrc/gpp_poll3.cuh):
- * `n_seg` plane segments per detection (0 = automatic, 1..32) and `resident_rows` rows of 64 planes kept in shared
- * memory (-1 = automatic, 0 = stream everything from L2).  Tests force the segmented and the streamed paths. */
+/* Schedule of the polling kernel (csrc/gpp_poll3.cuh): `n_seg` plane segments per detection (0 = automatic, 1..32)
+ * and, for the FAST / VERIFIED modes, `resident_rows` rows of 64 planes kept in shared memory (-1 = automatic, 0 =
+ * stream everything from L2).  Tests force the segmented and the streamed paths. */
 int gpp_debug_set_schedule(gpp_handle *h, int n_seg, int resident_rows);
 
 /* Runtime audit of the VERIFIED mode: with `every` = n > 0, each VERIFIED call re-polls every n-th detection in the

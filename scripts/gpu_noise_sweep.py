@@ -10,7 +10,6 @@ poller = gpp_b200.get_poller(0)
 dev = torch.device('cuda', 0)
 planes = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_22k.npy'))
 poller.set_planes(planes)
-poller.debug_set_config(int(os.environ.get('GPP_VARIANT', 0)), 0)      # 2 / 3 / 4: kernel variant with 2 / 3 / 4 CTAs per SM
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 modes = sys.argv[2:] or ['verified', 'fast']
 for noise in (0.0, 0.5, 1.5, 4.0, 10.0, 40.0):

@@ -1,5 +1,5 @@
-"""Development aid (round 2): kernel-only timings of the resident-database kernel against the round-1 ring kernels on the
-bench configurations, for schedule sweeps.  Run on the GPU box:  python scripts/gpu_r02_schedules.py > gpurun_out/x.json"""
+"""Development aid (round 2): kernel-only timings of the polling kernel on the bench configurations, for schedule sweeps
+(profiles/r02a_* were made with an earlier version that also timed the round-1 ring kernels, since removed).  Run on the GPU box:  python scripts/gpu_r02_schedules.py > gpurun_out/x.json"""
 import json
 import os
 import sys
@@ -45,14 +45,9 @@ def main():
         poller.set_planes(pl)
         hyp = B * 100.0 * pl.shape[0]
         res = {}
-        for mode in ('verified', 'fast'):
+        for mode in ('verified', 'fast', 'exact'):
             med, best = time_mode(poller, args, mode)
             res[mode + '_auto'] = {'ms': med, 'ms_min': best, 'hyp_per_s': hyp / (med * 1e-3)}
-            if not quick:
-                poller.debug_set_config(4 if mode == 'verified' else 3, 0)          # round-1 kernels (automatic split choice)
-                med, best = time_mode(poller, args, mode)
-                poller.debug_set_config(0, 0)
-                res[mode + '_ring_r01'] = {'ms': med, 'ms_min': best, 'hyp_per_s': hyp / (med * 1e-3)}
         if not quick:
             sweeps = [(1, 0), (1, 64), (1, 128), (1, -1)] if B >= 512 else [(1, 0), (2, 0), (4, 0), (8, 0), (16, 0), (32, 0), (2, -1), (4, -1), (32, -1)]
             for n_seg, resid in sweeps:

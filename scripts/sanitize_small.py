@@ -10,16 +10,21 @@ from oracle import c_oracle
 
 planes = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_10k.npy'))[:2500]
 poller = gpp_b200.get_poller(0)
-for (B, D, nv, force) in ((2, 20, 15, 0), (40, 50, None, 200), (3, 9, 7, 100)):
+for (B, D, nv, seg, resid) in ((2, 20, 15, 0, -1), (40, 50, None, 1, 7), (3, 9, 7, 5, 0), (200, 30, 25, 0, -1)):
     boxes, dims, orient, P_inv = synthetic.synth_detections(B, D, planes, seed=B, n_valid=nv)
     dims = dims.copy(); dims[0, :3, 1] *= 1.7
     want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
-    poller.debug_set_config(force, 0)
+    poller.debug_set_schedule(seg, resid)
     for mode in ('verified', 'exact', 'fast', 'f64'):
         got = gpp_b200.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True)
         if mode in ('verified', 'exact'):
             assert all(np.array_equal(g, w, equal_nan=True) for g, w in zip(got, want)), (mode, B, D)
-    poller.debug_set_config(0, 0)
+    gpp_b200.fit_road_planes(boxes, dims, orient, P_inv, planes, return_pose=True, return_kitti=True)
+    poller.debug_set_schedule(0, -1)
+poller.audit_set(3)
+gpp_b200.fit_road_planes(boxes, dims, orient, P_inv, planes)
+poller.audit_set(0)
+assert poller.audit_counts()[1] == 0
 kp = got[0].astype(np.float32).reshape(-1, 12)
 loc, ang, dd = gpp_b200.recover_pose(kp, dims.reshape(-1, 3), orient.reshape(-1))
 gpp_b200.kitti_records(loc, ang, dd)

@@ -39,7 +39,7 @@ def test_debug_hooks_are_not_part_of_the_drop_in_header():
     public = _declared_symbols('gpp.h')
     assert not [s for s in public if s.startswith(('gpp_debug_', 'gpp_microbench', 'gpp_audit_'))]
     dbg = _declared_symbols('gpp_debug.h')
-    for must in ('gpp_microbench', 'gpp_debug_set_config', 'gpp_debug_scores', 'gpp_debug_set_schedule',
+    for must in ('gpp_microbench', 'gpp_debug_scores', 'gpp_debug_set_schedule',
                  'gpp_audit_set', 'gpp_audit_counts'):
         assert must in dbg
 

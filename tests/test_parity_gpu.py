@@ -49,17 +49,16 @@ def test_exact_mode_is_bit_identical_to_the_oracle(gpp, tag, B, D, seed):
 
 
 def test_exact_mode_config3_full(gpp, poller):
-    """Config 3 shape (64 x 100 x 10k), every row checked; also with a forced 1-CTA-per-SM grid (longer
-    per-CTA tile streams, more ring wrap-arounds)."""
+    """Config 3 shape (64 x 100 x 10k), every row checked; automatic schedule and one segment per detection."""
     planes = load_planes('10k')
     boxes, dims, orient, P_inv = synthetic.synth_detections(64, 100, planes, seed=33)
     want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
-    for cps in (0, 1):
-        poller.debug_set_config(0, cps)
+    for n_seg in (0, 1):
+        poller.debug_set_schedule(n_seg, -1)
         try:
             got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='exact', return_index=True)
         finally:
-            poller.debug_set_config(0, 0)
+            poller.debug_set_schedule(0, -1)
         _assert_identical(got, want)
 
 

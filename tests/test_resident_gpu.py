@@ -1,7 +1,8 @@
-"""GPU: the resident-database kernel (csrc/gpp_poll3.cuh, default of the 'verified' and 'fast' modes) under every
-schedule it can take -- detections cut into plane segments, the database resident in shared memory / streamed from
-L2 / half and half, rows that repeat the previous row written by the warp that polled the first of them -- must
-return what the oracle returns, bit for bit ('verified') or up to rounding-noise ties ('fast')."""
+"""GPU: the polling kernel (csrc/gpp_poll3.cuh, all four modes) under every schedule it can take -- detections cut into
+plane segments, the pair database resident in shared memory / streamed from L2 / half and half, rows that repeat the
+previous row written by the warp that polled the first of them -- must return what the oracle returns, bit for bit
+('verified', 'exact', 'f64' against the FP64 oracle) or up to rounding-noise ties ('fast'); the fused pose / KITTI
+epilogue must equal the stand-alone kernels bit for bit."""
 import numpy as np
 import pytest
 
@@ -34,15 +35,22 @@ def test_every_schedule_equals_the_oracle(gpp, poller, n_seg, resident):
     planes = load_planes('10k')[:7001]                     # ragged last row, duplicate planes of the 10k database
     boxes, dims, orient, P_inv = _hard_batch(planes)
     want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    want64 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True, dtype=np.float64)
     poller.debug_set_schedule(n_seg, resident)
     try:
         got = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True)
         fast = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='fast', return_index=True)
+        exact = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='exact', return_index=True)
+        f64 = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64', return_index=True)
         few = gpp.fit_road_planes(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes, mode='verified',
                                   return_index=True)
     finally:
         poller.debug_set_schedule(0, -1)
     _same(got, want)
+    _same(exact, want)
+    assert np.array_equal(f64[3], want64[3])
+    assert np.allclose(f64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(f64[2], want64[2], equal_nan=True)
     _same(few, c_oracle.fit_road_planes_c(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes,
                                           return_index=True))
     valid = orient >= 0                      # padding rows are degenerate: pure rounding-noise ties
@@ -80,9 +88,9 @@ def test_repeated_calls_leave_the_counters_clean(gpp, poller):
         _same(got, want)
 
 
-def test_large_batch_resident_equals_ring_kernel(gpp, poller):
-    """automatic schedule of a large batch (one segment, 216 resident rows + streamed rest) against the round-1 ring
-    kernel and the EXACT kernel on 300 images x 100 rows x 21634 planes"""
+def test_large_batch_automatic_schedule_equals_exact(gpp):
+    """automatic schedule of a large batch (one segment, 212 resident rows + streamed rest) against the EXACT mode on
+    300 images x 100 rows x 21634 planes"""
     import torch
     planes = load_planes('22k')
     boxes, dims, orient, P_inv = synthetic.synth_detections(300, 100, planes, seed=9, n_valid=93)
@@ -90,15 +98,46 @@ def test_large_batch_resident_equals_ring_kernel(gpp, poller):
     args = [torch.from_numpy(a).to(dev) for a in (boxes, dims, orient, P_inv.astype(np.float32))]
     new = gpp.fit_road_planes_torch(*args, planes, mode='verified', return_index=True)
     ex = gpp.fit_road_planes_torch(*args, planes, mode='exact', return_index=True)
-    poller.debug_set_config(204, 0)
-    try:
-        old = gpp.fit_road_planes_torch(*args, planes, mode='verified', return_index=True)
-    finally:
-        poller.debug_set_config(0, 0)
     torch.cuda.synchronize()
-    for a, b, c in zip(new, old, ex):
-        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+    for a, c in zip(new, ex):
         assert np.array_equal(a.cpu().numpy(), c.cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize('mode', ['verified', 'exact', 'fast'])
+@pytest.mark.parametrize('n_seg', [0, 4])
+def test_fused_pose_epilogue_equals_the_stand_alone_kernels(gpp, poller, mode, n_seg):
+    """return_pose / return_kitti (pose recovery and the KITTI record in the polling kernel's epilogue, one launch)
+    against recover_pose / kitti_records on the polled key-points: the same device functions, the same bits -- incl.
+    padding rows (orientation -1: zeros, input dimensions) and rows that are copies of their predecessor"""
+    import torch
+    planes = load_planes('1k')
+    boxes, dims, orient, P_inv = _hard_batch(planes, seed=5)
+    poller.set_planes(planes)                                         # (the database upload has launches of its own)
+    poller.debug_set_schedule(n_seg, -1)
+    try:
+        launches = poller.launch_count()
+        full = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True, return_pose=True,
+                                   return_kitti=True)
+        assert poller.launch_count() - launches == 1                  # one kernel for polling + pose + KITTI record
+        dev = torch.device('cuda', 0)
+        t = gpp.fit_road_planes_torch(torch.from_numpy(boxes).to(dev), torch.from_numpy(dims).to(dev),
+                                      torch.from_numpy(orient).to(dev), torch.from_numpy(P_inv.astype(np.float32)).to(dev),
+                                      planes, mode=mode, return_pose=True, return_kitti=True)
+    finally:
+        poller.debug_set_schedule(0, -1)
+    base = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True)
+    assert len(full) == 8 and len(t) == 7
+    _same(full[:4], base)
+    loc, ang, dout = gpp.recover_pose(base[0].reshape(-1, 12), dims.reshape(-1, 3), orient.reshape(-1))
+    rec = gpp.kitti_records(loc, ang, dout)
+    shape = orient.shape
+    for got, want in zip(full[4:], (loc, ang, dout, rec)):
+        assert got.shape == shape + (want.shape[1],) and got.dtype == np.float32
+        assert np.array_equal(got.reshape(want.shape), want, equal_nan=True)
+    for a, b in zip(t[3:], full[4:]):
+        assert np.array_equal(a.cpu().numpy(), b, equal_nan=True)
+    assert np.all(full[4][orient < 0] == 0) and np.all(full[5][orient < 0] == 0)
+    assert np.array_equal(full[6][orient < 0], dims[orient < 0])
 
 
 def test_runtime_audit_counts(gpp, poller):

@@ -155,30 +155,6 @@ def test_padding_rows_are_polled_once_and_copied(gpp):
     assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
 
 
-@pytest.mark.parametrize('force', [100, 200])
-def test_small_batch_split_kernels_equal_oracle(gpp, poller, force):
-    """One detection per CTA with the planes split over the warps (small batches) vs the batch kernels: both
-    forced on the same inputs, every mode, incl. ragged N, padding rows and detections without six votes."""
-    planes = load_planes('22k')[:5003]
-    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 40, planes, seed=404, n_valid=33)
-    dims = dims.copy()
-    dims[1, :10, 1] *= 1.7
-    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
-    want64 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True, dtype=np.float64)
-    poller.debug_set_config(force, 0)
-    try:
-        for mode in ('exact', 'verified'):
-            _same(gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=mode, return_index=True), want)
-        got64 = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='f64', return_index=True)
-        fast = gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='fast', return_index=True)
-    finally:
-        poller.debug_set_config(0, 0)
-    assert np.array_equal(got64[3], want64[3])
-    assert np.allclose(got64[0], want64[0], rtol=1e-12, atol=0, equal_nan=True)
-    valid = orient >= 0          # padding rows are degenerate (all key-points equal): pure rounding-noise ties
-    assert np.mean(fast[3][valid] == want[3][valid]) > 0.97
-
-
 @pytest.mark.parametrize('ray_scale', [1.0, 1000.0, 1e-3])
 def test_verified_is_robust_to_ray_scale_and_odd_geometry(gpp, poller, ray_scale):
     """The margin must not depend on how P_inv happens to be scaled (rays are only defined up to a factor), and
@@ -208,24 +184,3 @@ def test_verified_is_robust_to_ray_scale_and_odd_geometry(gpp, poller, ray_scale
         s3_exact = _oracle_bottom3(boxes, dims, orient, P_scaled, planes, b, d)
         fin = np.isfinite(s3_exact) & np.isfinite(out[1])
         assert (np.abs(out[1][fin] - s3_exact[fin]) <= out[3][fin]).all()         # stage-1 margin, odd geometry
-
-
-@pytest.mark.parametrize('variant', [2, 3, 4])
-def test_every_verified_batch_kernel_variant_equals_the_oracle(gpp, poller, variant):
-    """The verified batch kernels -- group-synchronous with 2 / 3 CTAs per SM (variants 2, 3) and the default with
-    per-warp claiming and a rotated scan (variant 4) -- forced on inputs with padding rows, detections without six
-    votes, duplicates in the database and fewer detections than warps."""
-    planes = load_planes('10k')[:7001]                     # ragged last tile, duplicate rows of the 10k database
-    boxes, dims, orient, P_inv = synthetic.synth_detections(9, 60, planes, seed=505, n_valid=41, kp_noise_px=4.0)
-    dims = dims.copy()
-    dims[2, :12, 0] *= 1.6
-    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
-    poller.debug_set_config(200 + variant, 0)
-    try:
-        _same(gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode='verified', return_index=True), want)
-        few = gpp.fit_road_planes(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes, mode='verified',
-                                  return_index=True)
-        _same(few, c_oracle.fit_road_planes_c(boxes[:1, :3], dims[:1, :3], orient[:1, :3], P_inv[:1], planes,
-                                              return_index=True))
-    finally:
-        poller.debug_set_config(0, 0)
