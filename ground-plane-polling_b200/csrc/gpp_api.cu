@@ -362,6 +362,9 @@ int gpp::Staging::reserve(size_t bytes) {
     if (bytes <= cap) return GPP_OK;
     release();
     GPP_CUDA(cudaMalloc(reinterpret_cast<void **>(&base), bytes));
+    // a staged chunk leaves the device in ONE copy that spans the alignment gaps between its arrays: give those bytes
+    // a defined value once (compute-sanitizer initcheck otherwise flags every such copy)
+    GPP_CUDA(cudaMemset(base, 0, bytes));
     cap = bytes;
     return GPP_OK;
 }

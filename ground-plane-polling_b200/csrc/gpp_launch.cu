@@ -103,7 +103,9 @@ void release_poll3(gpp_handle *h) {
 
 // Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below three detections per resident warp every
 // detection is cut into plane segments so that the work items still fill the machine about three times over (the
-// last wave is then short whatever the batch size; at most 16: a single image is fastest with 16).  Residency:
+// last wave is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs
+// three times the average -- is long enough to be the tail; at most 32).  Tried and dropped (r02): whole rows first
+// and segments only for the last partial wave (64 x 100 x 10k: 0.32 ms against 0.26 ms).  Residency:
 // staging up to 212 KB per SM pays as soon as every warp polls a few items; a call with fewer items than that streams
 // every row from L2 and starts at once.
 static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride, cudaStream_t s) {
@@ -127,7 +129,6 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     int n_seg = 1;
     if (h->force_seg > 0) n_seg = h->force_seg;
     else if (n_rows < 3 * slots) n_seg = (int)((3 * slots + n_rows - 1) / n_rows);
-    if (n_seg > 16 && h->force_seg <= 0) n_seg = 16;
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;
     if (n_rows > h->seg_det_cap || n_rows * n_seg > h->seg_items_cap) n_seg = 1;

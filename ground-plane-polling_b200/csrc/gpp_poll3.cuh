@@ -482,10 +482,11 @@ __host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
 
 // ------------------------------------------------------------------ EXACT / F64: scalar scan, one plane per lane
 // The hypothesis comes in two halves (gpp_math.cuh): once a plane with six votes is known, a plane matters only if its
-// residual sum does not exceed the warp's best six-vote residual; the sum of the three bottom-face residuals never
-// exceeds the full sum (rounded addition of non-negative terms is monotone; a NaN / inf sum never wins), so
-// (r1 + r2) + r3 > best for all 32 lanes ends the hypothesis after its first half -- X_t, one division and three
-// square roots are skipped for about three of four rows, and nothing that is kept changes by a bit.
+// residual sum does not exceed the warp's best six-vote residual.  No partial sum of the residuals exceeds the full
+// sum (rounded addition of non-negative terms is monotone; a NaN / inf sum never wins), so the hypothesis is built in
+// steps and dropped as soon as all 32 lanes are out: r3 > best after the points l and r (two of the four divisions,
+// one of the six square roots), (r1 + r2) + r3 > best after the point m; X_t, the last division and three square
+// roots are reached by about one row in four.  Nothing that is kept changes by a bit.
 template <class P>
 __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typename P::T4 *__restrict__ planes,
                                             const int p_begin, const int p_end, const int lane, const bool same_rays,
@@ -518,9 +519,12 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
         int V; T R; bool zneg;
         if (m6) {
             T rb[3];
-            hypothesis_bottom<P>(det, pl.x, pl.y, pl.z, pl.w, X, rb, zneg);
+            rb[2] = bottom_lr<P>(det, pl.x, pl.y, pl.z, pl.w, X);
+            if (!__any_sync(0xffffffffu, valid && !(rb[2] > wbest))) continue;
+            bottom_m<P>(det, pl.x, pl.y, pl.z, pl.w, X, rb);
             const T S3 = P::add(P::add(rb[0], rb[1]), rb[2]);
             if (!__any_sync(0xffffffffu, valid && !(S3 > wbest))) continue;
+            zneg = bottom_zneg<P>(X);
             hypothesis_top<P>(det, pl.x, pl.y, pl.z, X, rb, V, R);
             if (valid) st.update(V, R, zneg, j, highest);
             wbest = warp_min_value(st.M == 6 ? st.bestR : highest);
