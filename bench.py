@@ -5,7 +5,7 @@ bench.py -- ground-plane hypotheses/s (detections x planes) of the polling hot p
     python bench.py --gpus N --steps K --warmup W              (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (config.workload): BASELINE.json configs[3] = "C4": 4096 KITTI-size images x 100 synthetic
+Workload (config.workload): BASELINE.json configs[3] = "C4": 4096 DISTINCT KITTI-size images x 100 synthetic
 detections x road_planes_database_22k (21634 planes) PER GPU (weak scaling: images are sharded, the database is
 replicated, there is no collective on the data path -- SURVEY.md section 8.5).  A step is one pass of the hot
 path over that batch.
@@ -15,11 +15,20 @@ path over that batch.
                between steps (the working set is smaller than L2)
     e2e        the same metric through the public numpy-in/numpy-out call ``fit_road_planes`` (C ABI
                ``gpp_fit_host``) from PINNED HOST buffers, host->device and device->host copies inside the
-               timed region, wall clock between barriers
+               timed region, wall clock between barriers;  e2e_pageable: the same from plain numpy arrays into
+               fresh result arrays (the drop-in call as the reference's callers would make it)
+    parity_*   the first 8 images of the LAST TIMED step against the C oracle (rank 0)
     roofline   FP32 CUDA-core bound (this path is neither HBM- nor tensor-bound: 0.006 B/hypothesis):
                achieved = 148 algorithmic FLOP/hypothesis (SURVEY.md section 8.4) x hypotheses / kernel time;
                peak = FFMA rate measured by libgpp's microbenchmark in this same run (MEASURED_PEAKS.json has no
-               FP32 entry), nominal 74.4 TFLOP/s beside it
+               FP32 entry), nominal 74.4 TFLOP/s beside it; FMA-pipe / MUFU / issue-slot utilisation and DRAM traffic
+               from the committed ncu capture of the same launch (profiles/)
+    strong     N > 1: BASELINE.json's multi-GPU configuration itself -- the 4096 images of C4 SHARDED over the N ranks
+               (kernel and end-to-end, time = max over ranks, efficiency against the one-GPU time of the same run)
+    multi_gpu_single_process   more than one visible GPU: one caller driving all of them (gpp_fit_host_multi), from
+               pinned and from pageable host arrays, rank 0 while the other ranks wait on the host
+    other_workloads   N = 1: C3, C2 and the reference's own call shape (one image, with and without padding rows):
+               kernel time, numpy-call latency, roofline fraction
     cpu_baseline  the oracle port (numpy restatement of the reference graph) timed on this box's host cores
                on a bounded sample of the same workload
 

@@ -101,8 +101,9 @@ def check(rc, what):
 
 
 def ptr(a):
-    """Raw data pointer of a C-contiguous numpy array (or None)."""
+    """Raw data address of a C-contiguous numpy array (or None) for a ``c_void_p`` argument.  (The plain integer:
+    ``ndarray.ctypes.data_as`` costs 2.6 us per array, which adds up to a fifth of a single-image call.)"""
     if a is None:
         return None
     assert isinstance(a, np.ndarray) and a.flags['C_CONTIGUOUS']
-    return a.ctypes.data_as(c_void_p)
+    return a.ctypes.data

@@ -1,14 +1,14 @@
 // The polling kernel (all four arithmetic modes) -- since round 2 the only one.
 //
-// The ring kernels (gpp_poll2.cuh) stream the database through ONE tile ring per CTA, so the eight warps of a CTA
-// run at the pace of their slowest detection (~20 % of the warp time was spent waiting for the next tile).  Here no
-// two warps share anything:
-//   * one persistent CTA per SM; the first `resident_rows` rows (1 row = 32 plane pairs = 1 KB) of the
-//     pair-interleaved database are staged ONCE per CTA into shared memory by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier, SASS UBLKCP) -- up to 216 KB, i.e. 13.8k of the 21.6k planes of the largest shipped
-//     database, all of the smaller ones;
+// Round 1 streamed the database through ONE tile ring per CTA, so the eight warps of a CTA ran at the pace of their
+// slowest detection (~20 % of the warp time was spent waiting for the next tile).  Here no two warps share anything:
+//   * one persistent CTA per SM (32 warps at 64 registers; fp64: 16 at 128); the first `resident_rows` rows (1 row =
+//     32 plane pairs = 64 planes = 1 KB) of the pair-interleaved database are staged ONCE per CTA into shared memory by
+//     1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) -- up to 212 KB, i.e. 13.5k of the 21.6k planes of
+//     the largest shipped database, all of the smaller ones;
 //   * the remaining rows are read by each warp straight from L2 (the database never leaves L2), one row ahead of
-//     its use (register prefetch, ld.global.nc), so that the L2 latency hides behind the previous row's arithmetic;
+//     its use (in-place register prefetch, ld.global.nc), so that the L2 latency hides behind the previous row's
+//     arithmetic;
 //   * every warp claims its own work items from a device counter.  An item is (detection, plane segment): large
 //     batches use one segment per detection, small batches cut every detection into up to 32 segments so that a
 //     single image still fills the 148 SMs; the warp that finishes the last segment of a detection merges the
@@ -18,9 +18,9 @@
 //     call, no work lists, no memset: the counters are reset by the last warp / CTA that uses them.
 // Modes: FAST and VERIFIED scan the pair-interleaved database with the packed arithmetic of gpp_poll2.cuh; EXACT
 // (fp32) and F64 scan the plain database with the scalar hypothesis of gpp_math.cuh, one plane per lane, straight from
-// L2 (they are bound by their own arithmetic: 155 / 300 instructions per 16 / 32 bytes).  The epilogue can run the two
-// steps that follow polling in the reference's driver -- pose recovery and the KITTI record (gpp_pose.cuh) -- on the
-// winner it has just recomputed.
+// L2 (they are bound by their own arithmetic: ~165 / ~300 instructions per 16 / 32 bytes).  The epilogue can run the
+// two steps that follow polling in the reference's driver -- pose recovery and the KITTI record (gpp_pose.cuh) -- on
+// the winner it has just recomputed (fit_road_planes.py:49-139, bin/run_network.py:137-247, :297-327).
 #pragma once
 #include <type_traits>
 
@@ -43,7 +43,7 @@ enum { kModeFast = 0, kModeVerified = 1, kModeExact = 2, kModeF64 = 3 };
 struct PollArgs3 {
     const float *boxes, *dims, *pinv;
     const int32_t *orient;
-    const u64 *pairs;            // pair-interleaved normalised fp32 DB (see PollArgs2): FAST / VERIFIED scans
+    const u64 *pairs;            // pair-interleaved normalised fp32 DB, {a0,a1,b0,b1,c0,c1,d0,d1} per pair: FAST / VERIFIED
     const float4 *planes;        // plain normalised fp32 DB: exact paths, EXACT scan
     const double4 *planes64;     // fp64 DB: F64 scan
     int n_planes, n_pairs_padded, dets_per_image;

@@ -66,7 +66,7 @@ class PlanePoller(object):
         if p.dtype not in (np.float32, np.float64) or not (p.flags['C_CONTIGUOUS'] or p.flags['F_CONTIGUOUS']):
             p = _f32(p)
         order = 0 if p.flags['C_CONTIGUOUS'] else 1
-        rc = self._lib.gpp_set_planes_raw(self._h, p.ctypes.data_as(ctypes.c_void_p), p.shape[0],
+        rc = self._lib.gpp_set_planes_raw(self._h, p.ctypes.data, p.shape[0],
                                           1 if p.dtype == np.float64 else 0, order)
         _lib.check(rc, 'gpp_set_planes_raw')
         self._dev_planes = None

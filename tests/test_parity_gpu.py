@@ -199,6 +199,64 @@ def test_device_entry_and_dlpack(gpp):
     _assert_identical([o.cpu().numpy() for o in out2], want)
 
 
+def test_torch_database_is_never_stale(gpp, poller):
+    """A fresh CUDA tensor per call with different content must be polled against ITS content, also when the caching
+    allocator hands it the block (data_ptr, shape, version 0) of the tensor before it; an in-place update of the same
+    tensor must be seen; a database updated on one stream must be seen by a fit on another."""
+    import torch
+    dev = torch.device('cuda', 0)
+    base = load_planes('1k').astype(np.float32)
+    dbs = [np.ascontiguousarray(base[k * 200:(k + 1) * 200]) for k in range(4)]
+    boxes, dims, orient, P_inv = synthetic.synth_detections(2, 30, base, seed=73)
+    t = [torch.from_numpy(a).to(dev) for a in (boxes, dims, orient, P_inv.astype(np.float32))]
+    ptrs = set()
+    for db in dbs + dbs[::-1]:
+        planes = torch.from_numpy(db).to(dev)                    # same size every time: the allocator recycles blocks
+        ptrs.add(planes.data_ptr())
+        out = gpp.fit_road_planes_torch(*t, planes, mode='exact', return_index=True)
+        want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, db, return_index=True)
+        _assert_identical([o.cpu().numpy() for o in out], want)
+        del planes, out
+    assert len(ptrs) < 8                                         # the scenario did occur: addresses were reused
+    planes = torch.from_numpy(dbs[0]).to(dev)
+    gpp.fit_road_planes_torch(*t, planes, mode='exact')
+    planes.copy_(torch.from_numpy(dbs[1]).to(dev))               # in place: same object, new version
+    out = gpp.fit_road_planes_torch(*t, planes, mode='exact', return_index=True)
+    _assert_identical([o.cpu().numpy() for o in out], c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, dbs[1], return_index=True))
+    side = torch.cuda.Stream(device=dev)
+    planes2 = torch.from_numpy(dbs[2]).to(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        poller.set_planes_torch(planes2)                         # database updated on the side stream ...
+    out = poller.fit_torch(*t, mode='exact', return_index=True)  # ... polled on the current one
+    torch.cuda.synchronize()
+    _assert_identical([o.cpu().numpy() for o in out], c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, dbs[2], return_index=True))
+    # one database per call: an expand()ed view is one, a materialised tile is refused without touching the device
+    tiled = planes2.unsqueeze(0).expand(2, -1, -1)
+    out = gpp.fit_road_planes_torch(*t, tiled, mode='exact', return_index=True)
+    _assert_identical([o.cpu().numpy() for o in out], c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, dbs[2], return_index=True))
+    with pytest.raises(ValueError):
+        gpp.fit_road_planes_torch(*t, tiled.contiguous(), mode='exact')
+
+
+def test_tiled_numpy_databases_are_grouped_exactly(gpp):
+    """(B, N, 4) databases as preprocessing/kitti.py:220 tiles them: one upload for a true tile, per-image groups when
+    one image's copy differs in a single value"""
+    from gpp_b200.layers.fit_road_planes import _plane_groups
+    db = load_planes('100')
+    tile = np.tile(db[None], (6, 1, 1))
+    assert [(a, b) for a, b, _ in _plane_groups(tile, 6)] == [(0, 6)]
+    assert [(a, b) for a, b, _ in _plane_groups(np.broadcast_to(db, (6,) + db.shape), 6)] == [(0, 6)]
+    tile[3, 57, 2] = np.nextafter(tile[3, 57, 2], 1.0)
+    assert [(a, b) for a, b, _ in _plane_groups(tile, 6)] == [(0, 3), (3, 4), (4, 6)]
+    assert [(a, b) for a, b, _ in _plane_groups(np.asfortranarray(tile), 6)] == [(0, 3), (3, 4), (4, 6)]
+    boxes, dims, orient, P_inv = synthetic.synth_detections(6, 20, db, seed=75)
+    got = gpp.fit_road_planes(boxes, dims, orient, P_inv, tile, mode='exact', return_index=True)
+    want = [c_oracle.fit_road_planes_c(boxes[b:b + 1], dims[b:b + 1], orient[b:b + 1], P_inv[b:b + 1], tile[b], return_index=True)
+            for b in range(6)]
+    _assert_identical(got, [np.concatenate([w[i] for w in want], axis=0) for i in range(4)])
+
+
 def test_database_reupload_is_skipped_and_switching_works(gpp, poller):
     p1, p2 = load_planes('100'), load_planes('1k')
     boxes, dims, orient, P_inv = synthetic.synth_detections(1, 10, p1, seed=71)
