@@ -25,7 +25,7 @@ path over that batch.
                from the committed ncu capture of the same launch (profiles/)
     strong     N > 1: BASELINE.json's multi-GPU configuration itself -- the 4096 images of C4 SHARDED over the N ranks
                (kernel and end-to-end, time = max over ranks, efficiency against the one-GPU time of the same run)
-    multi_gpu_single_process   more than one visible GPU: one caller driving all of them (gpp_fit_host_multi), from
+    multi_gpu_single_process   N > 1: one caller driving all N GPUs (gpp_fit_host_multi), from
                pinned and from pageable host arrays, rank 0 while the other ranks wait on the host
     other_workloads   N = 1: C3, C2 and the reference's own call shape (one image, with and without padding rows):
                kernel time, numpy-call latency, roofline fraction
@@ -414,8 +414,8 @@ def main():
     if world > 1:
         barrier()
         dist.barrier(group=host_group)
-    if rank == 0 and n_vis > 1:
-        devs = list(range(min(n_vis, max(world, 2)))) if world > 1 else list(range(n_vis))
+    if rank == 0 and world > 1 and n_vis >= world:
+        devs = list(range(world))                             # exactly the GPUs this job was given
         for d in devs:
             gpp_b200.get_poller(d).set_planes(planes)
         multi = {'devices': len(devs)}
