@@ -112,7 +112,8 @@ def test_fused_pose_epilogue_equals_the_stand_alone_kernels(gpp, poller, mode, n
     import torch
     planes = load_planes('1k')
     boxes, dims, orient, P_inv = _hard_batch(planes, seed=5)
-    poller.set_planes(planes)                                         # (the database upload has launches of its own)
+    poller.set_planes(planes)                                         # (the database upload has launches of its own,
+    poller.audit_set(0)                                               # and so has the audit pass if GPP_AUDIT is set)
     poller.debug_set_schedule(n_seg, -1)
     try:
         launches = poller.launch_count()
