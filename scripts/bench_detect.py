@@ -50,6 +50,8 @@ bytes_dec = B * A * 4 * (12 + 8 + 3 + 12 + 3) + A * 16
 ms_fil, det = timed(lambda: gpp_b200.filter_detections_torch(boxes, dims, cls))
 bytes_fil = B * A * 4 * 8 + B * A            # classification read + orientation byte written (the dominant traffic)
 ms_all, out = timed(lambda: gpp_b200.detections_from_heads(anchors, reg, rdim, cls, P_inv, planes))
+ms_pose, out = timed(lambda: gpp_b200.detections_from_heads(anchors, reg, rdim, cls, P_inv, planes, return_pose=True,
+                                                          return_kitti=True))
 res = {
     'anchors_per_image': A, 'images': B,
     'decode': {'ms': ms_dec, 'anchors_per_s': B * A / ms_dec * 1e3, 'algorithmic_bytes': bytes_dec,
@@ -58,9 +60,11 @@ res = {
                'score_pass_algorithmic_bytes': bytes_fil, 'score_pass_gbs_if_alone': bytes_fil / ms_fil / 1e6},
     'tail_heads_to_polled_detections': {'ms': ms_all, 'images_per_s': B / ms_all * 1e3,
                                         'note': 'decode + filter + polling of 100 rows/image x 21634 planes (verified mode)'},
+    'tail_with_pose_and_kitti_record': {'ms': ms_pose, 'images_per_s': B / ms_pose * 1e3,
+                                        'note': 'the same with pose recovery and the KITTI record in the polling epilogue (4 launches)'},
     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
 }
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-with open(os.path.join(ROOT, 'gpurun_out', 'bench_detect.json'), 'w') as f:
+with open(os.path.join(ROOT, 'gpurun_out', 'bench_detect_%d.json' % B), 'w') as f:
     json.dump(res, f, indent=1)
 print(json.dumps(res, indent=1))
