@@ -108,8 +108,8 @@ constexpr int kNmsThreads = 512;
 constexpr int kNmsSmemKeys = 4096;      // candidate lists up to this size are sorted in shared memory
 constexpr int kMaxDet = 128;
 
-// One CTA per image: bitonic sort of the candidate keys, greedy NMS in sorted order by warp 0 (a candidate is kept
-// iff its IoU with every box kept so far is <= the threshold; stops at max_detections), gather + pad with -1.
+// One CTA per image: bitonic sort of the candidate keys, greedy NMS in sorted order (a candidate is kept iff its IoU
+// with every box kept so far is <= the threshold; stops at max_detections), gather + pad with -1.
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const float *__restrict__ boxes, const float *__restrict__ dims,
                                                           const unsigned char *__restrict__ orient, int A,
                                                           unsigned long long *__restrict__ keys_all, long long key_stride,
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const float *__restric
                                                           int32_t *__restrict__ out_labels, int32_t *__restrict__ out_orient) {
     __shared__ unsigned long long skeys[kNmsSmemKeys];
     __shared__ float4 sel_box[kMaxDet];
+    __shared__ float4 cand_box[kNmsThreads];
+    __shared__ unsigned int batch_mask[kNmsThreads / 32];
+    __shared__ unsigned char batch_alive[kNmsThreads / 32];
     __shared__ unsigned long long sel_key[kMaxDet];
     __shared__ int n_sel;
     const int b = blockIdx.x;
@@ -148,24 +151,45 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const float *__restric
     if (threadIdx.x == 0) n_sel = 0;
     __syncthreads();
     const float4 *boxes4 = reinterpret_cast<const float4 *>(boxes) + (long long)b * A * 3;   // first float4 = x1,y1,x2,y2
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int ns = 0;
-        for (int c = 0; c < K && ns < max_det; ++c) {
-            const unsigned long long key = keys[c];
-            const int a = (int)(key & 0xffffffffu);
-            const float4 cand = boxes4[3 * (long long)a];
+    // Greedy pass in sorted order: a candidate is kept iff no box kept before it overlaps it by more than the threshold.
+    // The chain is serial in the candidates, so it is walked 16 at a time: the candidates' boxes are gathered into
+    // shared memory by the whole CTA (kNmsThreads per gather); warp w tests candidate c0 + w against every box kept
+    // before the batch and against its batch-mates before it (a bit mask); one thread then resolves the batch in order
+    // with bit operations.  (One candidate at a time took 0.13 ms for one image with 300 candidates, r02n.)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kBatch = kNmsThreads / 32;
+    for (int g0 = 0; g0 < K && n_sel < max_det; g0 += kNmsThreads) {
+        const int gn = min(kNmsThreads, K - g0);
+        if ((int)threadIdx.x < gn) cand_box[threadIdx.x] = boxes4[3 * (long long)(keys[g0 + threadIdx.x] & 0xffffffffu)];
+        __syncthreads();
+        for (int c0 = 0; c0 < gn; c0 += kBatch) {
+            const int ns = n_sel;                          // CTA-uniform: written before the last barrier
+            if (ns >= max_det) break;
+            const int c = c0 + warp;
+            const bool valid = c < gn;
+            const float4 cand = cand_box[valid ? c : 0];
             bool hit = false;
-            for (int s = lane; s < ns; s += 32) hit = hit || iou_gt(cand, sel_box[s], nms_threshold);
-            if (!__any_sync(0xffffffffu, hit)) {
-                if (lane == 0) { sel_box[ns] = cand; sel_key[ns] = key; }
-                ++ns;
-                __syncwarp();
+            for (int sidx = lane; sidx < ns; sidx += 32) hit = hit || iou_gt(cand, sel_box[sidx], nms_threshold);
+            const bool alive = valid && !__any_sync(0xffffffffu, hit);
+            const bool mate = lane < warp && c0 + lane < gn;
+            const unsigned mask = __ballot_sync(0xffffffffu, mate && iou_gt(cand, cand_box[mate ? c0 + lane : 0], nms_threshold));
+            if (lane == 0) { batch_mask[warp] = mask; batch_alive[warp] = alive ? 1 : 0; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned kept = 0u;
+                int n = ns;
+                for (int w = 0; w < kBatch && n < max_det; ++w)
+                    if (batch_alive[w] && !(batch_mask[w] & kept)) {
+                        kept |= 1u << w;
+                        sel_box[n] = cand_box[c0 + w];
+                        sel_key[n] = keys[g0 + c0 + w];
+                        ++n;
+                    }
+                n_sel = n;
             }
+            __syncthreads();
         }
-        if (lane == 0) n_sel = ns;
     }
-    __syncthreads();
     const int ns = n_sel;
     // gather (filter_detections.py:163-168) and pad with -1 (:170-177); 17 values per output row
     for (int t = threadIdx.x; t < max_det * 17; t += blockDim.x) {
