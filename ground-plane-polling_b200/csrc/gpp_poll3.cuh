@@ -649,17 +649,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             if (kVerified) {
                 VerifiedScan sc;
                 sc.begin();
+                // segments of one detection share their bounds: every fourth row a warp publishes its own (one atomicMax
+                // on the detection's 64-bit key) and adopts the best published so far (one uniform branch per row; the
+                // round-2 profile of C3 showed the per-row form of this exchange at 40 instructions a row)
                 for (; src.rows_left > 0; src.advance()) {
-                    // segments of one detection share their bounds: the key is fetched here and used after the row
-                    const bool share = kSeg && (src.rows_left & 3) == 0;
-                    unsigned long long key = 0ull;
-                    if (share) key = *reinterpret_cast<volatile unsigned long long *>(args.seg_best + slot);
-                    const int Mb = sc.Mcur;
-                    const float wb = sc.wbest;
                     sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
-                    if (kSeg && (sc.Mcur != Mb || sc.wbest < wb) && lane == 0)
-                        atomicMax(args.seg_best + slot, seg_key(sc.Mcur, sc.wbest));
-                    if (share) sc.adopt(key, detx);
+                    if (kSeg && (src.rows_left & 3) == 1) {
+                        unsigned long long key = seg_key(sc.Mcur, sc.wbest);
+                        if (lane == 0) key = max(key, atomicMax(args.seg_best + slot, key));
+                        sc.adopt(__shfl_sync(0xffffffffu, key, 0), detx);
+                    }
                 }
                 sc.finish(detx, args.planes, queue, lane);
                 sc.result(Mw, rb, idx);
