@@ -1,8 +1,8 @@
 """Small run of every kernel path for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck python scripts/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py   (it checks against the oracle, hence under tests/)"""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import gpp_b200
 from gpp_b200.utils import synthetic
