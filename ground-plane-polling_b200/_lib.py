@@ -62,6 +62,7 @@ SIGNATURES = {
     'gpp_launch_count': (ctypes.c_int64, [c_void_p]),
     'gpp_microbench': (c_int, [c_void_p, c_int, c_double_p, c_float_p, c_double_p]),
     'gpp_debug_set_schedule': (c_int, [c_void_p, c_int, c_int]),
+    'gpp_debug_scan_order': (c_int, [c_void_p, c_int, c_void_p]),
     'gpp_audit_set': (c_int, [c_void_p, c_int]),
     'gpp_audit_counts': (c_int, [c_void_p, c_int64_p, c_int64_p]),
     'gpp_debug_scores': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

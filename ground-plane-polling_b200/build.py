@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libgpp.so')
-SOURCES = ['gpp_api.cu', 'gpp_launch.cu', 'gpp_pose.cu', 'gpp_detect.cu', 'gpp_microbench.cu']
+SOURCES = ['gpp_api.cu', 'gpp_launch.cu', 'gpp_pose.cu', 'gpp_detect.cu', 'gpp_microbench.cu', 'gpp_order.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 NVCC_FLAGS = ARCH + ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -137,8 +137,10 @@ int gpp_destroy(gpp_handle *h) {
     cudaDeviceSynchronize();
     cudaFree(h->d_raw);
     cudaFree(h->d_planes32);
+    cudaFree(h->d_planes32_scan);
     cudaFree(h->d_planes64);
     cudaFree(h->d_pairs);
+    cudaFree(h->d_scan_index);
     cudaFree(h->filter_keys);
     cudaFree(h->filter_orient);
     cudaFree(h->filter_counts);
@@ -164,9 +166,13 @@ static int ensure_plane_capacity(gpp_handle *h, int n) {
     if (n <= h->cap_planes) return GPP_OK;
     cudaFree(h->d_raw);
     cudaFree(h->d_planes32);
+    cudaFree(h->d_planes32_scan);
     cudaFree(h->d_planes64);
     cudaFree(h->d_pairs);
+    cudaFree(h->d_scan_index);
+    h->d_planes32_scan = nullptr;
     h->d_pairs = nullptr;
+    h->d_scan_index = nullptr;
     h->d_raw = nullptr;
     h->d_planes32 = nullptr;
     h->d_planes64 = nullptr;
@@ -174,13 +180,17 @@ static int ensure_plane_capacity(gpp_handle *h, int n) {
     h->n_planes = 0;
     GPP_CUDA(cudaMalloc(&h->d_raw, sizeof(float) * 4 * (size_t)n));
     GPP_CUDA(cudaMalloc(&h->d_planes32, sizeof(float4) * (size_t)n));
+    GPP_CUDA(cudaMalloc(&h->d_planes32_scan, sizeof(float4) * (size_t)n));
     GPP_CUDA(cudaMalloc(&h->d_planes64, sizeof(double4) * (size_t)n));
     GPP_CUDA(cudaMalloc(&h->d_pairs, 32 * (size_t)((n + 63) / 64) * 32));
+    GPP_CUDA(cudaMalloc(&h->d_scan_index, sizeof(int32_t) * 64 * (size_t)((n + 63) / 64)));
     h->cap_planes = n;
     return GPP_OK;
 }
 
-static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
+// `host_rows`: the database as fed (N x 4 float32, row-major) when the host has it -- the scan order of the pair
+// database is derived from it (gpp_order.cu); null = scan in index order
+static int normalise_on(gpp_handle *h, int n, const float *host_rows, cudaStream_t s) {
     const int threads = 128, blocks = (n + threads - 1) / threads;
     normalise_planes_kernel<gpp::ExactF32><<<blocks, threads, 0, s>>>(h->d_raw, n, h->d_planes32);
     normalise_planes_kernel<gpp::ExactF64><<<blocks, threads, 0, s>>>(h->d_raw, n, h->d_planes64);
@@ -188,7 +198,10 @@ static int normalise_on(gpp_handle *h, int n, cudaStream_t s) {
     GPP_CUDA(cudaGetLastError());
     h->n_planes = n;
     h->n_pairs_padded = ((n + 63) / 64) * 32;
-    return gpp::build_pairs(h, s);
+    if (!host_rows) return gpp::build_pairs(h, nullptr, s);
+    std::vector<int32_t> order;
+    gpp::scan_order(host_rows, n, order);
+    return gpp::build_pairs(h, order.data(), s);
 }
 
 // every launch that may still read the resident database has an event on record: wait for them on `s`
@@ -223,7 +236,7 @@ int gpp_set_planes_raw(gpp_handle *h, const void *planes, int n_planes, int dtyp
     if (rc) return rc;
     cudaStream_t s = h->streams[0];
     GPP_CUDA(cudaMemcpyAsync(h->d_raw, rows.data(), sizeof(float) * rows.size(), cudaMemcpyHostToDevice, s));
-    rc = normalise_on(h, n_planes, s);
+    rc = normalise_on(h, n_planes, rows.data(), s);
     if (rc) return rc;
     GPP_CUDA(cudaStreamSynchronize(s));
     h->n_planes = n_planes;
@@ -251,7 +264,18 @@ int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, vo
     int rc = ensure_plane_capacity(h, n_planes);
     if (rc) return rc;
     GPP_CUDA(cudaMemcpyAsync(h->d_raw, d_planes, sizeof(float) * 4 * (size_t)n_planes, cudaMemcpyDeviceToDevice, s));
-    rc = normalise_on(h, n_planes, s);
+    // The scan order is computed on the host (a k-d tree over the planes, ~1 ms): a database of 32 rows or more is read
+    // back once per update, which blocks the caller until `s` has caught up.  Inside a stream capture (no host round
+    // trip possible) and for small databases the pair database keeps the index order.
+    std::vector<float> host_rows;
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) cudaGetLastError();
+    if (n_planes >= 32 * 64 && capturing == cudaStreamCaptureStatusNone) {
+        host_rows.resize(4 * (size_t)n_planes);
+        GPP_CUDA(cudaMemcpyAsync(host_rows.data(), h->d_raw, sizeof(float) * host_rows.size(), cudaMemcpyDeviceToHost, s));
+        GPP_CUDA(cudaStreamSynchronize(s));
+    }
+    rc = normalise_on(h, n_planes, host_rows.empty() ? nullptr : host_rows.data(), s);
     if (rc) return rc;
     h->n_planes = n_planes;
     h->raw_valid = false;

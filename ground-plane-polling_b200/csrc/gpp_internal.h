@@ -54,8 +54,10 @@ struct gpp_handle {
     // copy padded to 64 planes (gpp_poll2.cuh)
     float *d_raw = nullptr;
     float4 *d_planes32 = nullptr;
+    float4 *d_planes32_scan = nullptr;       // d_planes32 in scan order (gpp_order.cu)
     double4 *d_planes64 = nullptr;
     unsigned long long *d_pairs = nullptr;
+    int32_t *d_scan_index = nullptr;         // [2 * n_pairs_padded] plane index of every position of d_pairs (gpp_order.cu)
     int n_pairs_padded = 0;
     int n_planes = 0, cap_planes = 0;
     // bytes of the last host upload as the caller passed them (gpp_set_planes_raw compares before doing any work)
@@ -112,7 +114,10 @@ namespace gpp {
 int configure_kernels(gpp_handle *h);
 void release_poll3(gpp_handle *h);
 void release_audit(gpp_handle *h);
-int build_pairs(gpp_handle *h, cudaStream_t s);
+// order[position] = plane index: the order in which the pair database is stored and scanned (gpp_order.cu)
+void scan_order(const float *rows, int n, std::vector<int32_t> &order);
+// fills d_scan_index (from `order`, or with the identity when it is null) and d_pairs from d_planes32, on `s`
+int build_pairs(gpp_handle *h, const int32_t *order, cudaStream_t s);
 // one polling call (any GPP_MODE_*) on device memory, enqueued on `s`; VERIFIED calls are followed by the audit pass
 // when the handle asks for it
 int launch_poll(gpp_handle *h, const FitIO &io, int mode, cudaStream_t s);

@@ -8,25 +8,45 @@
 
 namespace gpp {
 
-// pair-interleaved, padded copy of the normalised fp32 database: pair p = planes (2p, 2p+1) stored as
-// {a0,a1,b0,b1,c0,c1,d0,d1}; planes past N-1 are copies of plane N-1 (same score, higher index: they can
-// never win a first-occurrence arg-min and do not change max-votes)
-__global__ void interleave_pairs_kernel(const float4 *__restrict__ planes, int n, int n_pairs_padded,
-                                        float *__restrict__ pairs) {
+// pair-interleaved, padded copy of the normalised fp32 database in SCAN ORDER (gpp_order.cu): position q holds plane
+// scan_index[q]; pair p = positions (2p, 2p+1) stored as {a0,a1,b0,b1,c0,c1,d0,d1}.  Positions past N-1 are copies of
+// position N-1 (the scans never queue / select a position >= N).
+__global__ void scan_index_kernel(const int32_t *__restrict__ order, int n, int n_padded, int32_t *__restrict__ scan_index) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_padded) return;
+    const int src = min(q, n - 1);
+    scan_index[q] = order ? order[src] : src;
+}
+__global__ void interleave_pairs_kernel(const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index,
+                                        int n, int n_pairs_padded, float *__restrict__ pairs,
+                                        float4 *__restrict__ planes_scan) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs_padded) return;
-    const float4 a = planes[min(2 * p, n - 1)], b = planes[min(2 * p + 1, n - 1)];
+    const float4 a = planes[scan_index[2 * p]], b = planes[scan_index[2 * p + 1]];
     float4 *out = reinterpret_cast<float4 *>(pairs + 8 * (size_t)p);
     out[0] = make_float4(a.x, b.x, a.y, b.y);
     out[1] = make_float4(a.z, b.z, a.w, b.w);
+    if (2 * p < n) planes_scan[2 * p] = a;               // the plain database in scan order (EXACT scan)
+    if (2 * p + 1 < n) planes_scan[2 * p + 1] = b;
 }
 
-int build_pairs(gpp_handle *h, cudaStream_t s) {
-    const int np = h->n_pairs_padded;
-    interleave_pairs_kernel<<<(np + 127) / 128, 128, 0, s>>>(h->d_planes32, h->n_planes, np,
-                                                            reinterpret_cast<float *>(h->d_pairs));
-    h->launches += 1;
-    cudaError_t e = cudaGetLastError();
+int build_pairs(gpp_handle *h, const int32_t *order, cudaStream_t s) {
+    const int np = h->n_pairs_padded, n = h->n_planes;
+    cudaError_t e = cudaSuccess;
+    if (order) {
+        // staged in the (not yet written) pair buffer: 4 bytes per plane of its 16.  `order` is pageable host memory, so
+        // the call returns once it has been read.
+        int32_t *tmp = reinterpret_cast<int32_t *>(h->d_pairs) + 2 * (size_t)np;      // second quarter of the buffer
+        e = cudaMemcpyAsync(tmp, order, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return set_error(GPP_ECUDA, "scan order upload: %s", cudaGetErrorString(e));
+        scan_index_kernel<<<(2 * np + 127) / 128, 128, 0, s>>>(tmp, n, 2 * np, h->d_scan_index);
+    } else {
+        scan_index_kernel<<<(2 * np + 127) / 128, 128, 0, s>>>(nullptr, n, 2 * np, h->d_scan_index);
+    }
+    interleave_pairs_kernel<<<(np + 127) / 128, 128, 0, s>>>(h->d_planes32, h->d_scan_index, n, np,
+                                                            reinterpret_cast<float *>(h->d_pairs), h->d_planes32_scan);
+    h->launches += 2;
+    e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "interleave_pairs_kernel launch: %s", cudaGetErrorString(e));
     return GPP_OK;
 }
@@ -115,7 +135,7 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "polling slot: %s", cudaGetErrorString(e));
     PollArgs3 b;
     b.boxes = io.boxes; b.dims = io.dims; b.pinv = io.pinv; b.orient = io.orient;
-    b.pairs = h->d_pairs; b.planes = h->d_planes32; b.planes64 = h->d_planes64; b.n_planes = h->n_planes;
+    b.pairs = h->d_pairs; b.scan_index = h->d_scan_index; b.planes = h->d_planes32; b.planes_scan = h->d_planes32_scan; b.planes64 = h->d_planes64; b.n_planes = h->n_planes;
     b.n_pairs_padded = h->n_pairs_padded; b.dets_per_image = io.D; b.n_det = io.n_det;
     b.keypoints = io.keypoints; b.keyplanes = io.keyplanes; b.residuals = io.residuals; b.best = io.best;
     b.pose_locations = io.pose_locations; b.pose_angles = io.pose_angles; b.pose_dimensions = io.pose_dimensions;
@@ -132,8 +152,7 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;
     if (n_rows > h->seg_det_cap || n_rows * n_seg > h->seg_items_cap) n_seg = 1;
-    b.rows_per_seg = (NR + n_seg - 1) / n_seg;
-    b.n_seg = (NR + b.rows_per_seg - 1) / b.rows_per_seg;
+    b.n_seg = n_seg < 1 ? 1 : n_seg;
     const long long n_items = n_rows * b.n_seg;
     int res = 0;
     if (mode == GPP_MODE_FAST || mode == GPP_MODE_VERIFIED) {
@@ -149,15 +168,15 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     poll3_variant(mode, b.n_seg > 1, b.pose_locations != nullptr)<<<(unsigned)grid, warps * 32, smem, s>>>(b);
 #ifdef GPP_STATS
     if (mode == GPP_MODE_VERIFIED) {
-        unsigned long long st[8], zero[8] = {0};
+        unsigned long long st[10], zero[10] = {0};
         cudaDeviceSynchronize();
         cudaMemcpyFromSymbol(st, g_stats3, sizeof(st));
         cudaMemcpyToSymbol(g_stats3, zero, sizeof(zero));
         const double rows = double(st[0] + st[2]), items = double(st[5] ? st[5] : 1);
         fprintf(stderr, "[gpp stats3] items %llu (identical-rays %llu) seg %d resident %d: rows/item %.1f, all-six %.1f%% (past stage 1: %.1f%% "
-                "of them), general %.1f%%, rows with survivors %.2f%%; exact verifications/item %.1f, flushes/item %.2f\n",
+                "of them), general %.1f%% (at max-votes >= 4: %.1f%% past the bottom face), rows with survivors %.2f%%; exact verifications/item %.1f, flushes/item %.2f\n",
                 st[5], st[6], b.n_seg, res, rows / items, 100.0 * st[0] / (rows ? rows : 1), 100.0 * st[1] / (st[0] ? st[0] : 1),
-                100.0 * st[2] / (rows ? rows : 1), 100.0 * st[7] / (rows ? rows : 1), double(st[3]) / items, double(st[4]) / items);
+                100.0 * st[2] / (rows ? rows : 1), 100.0 * st[8] / (st[9] ? st[9] : 1), 100.0 * st[7] / (rows ? rows : 1), double(st[3]) / items, double(st[4]) / items);
     }
 #endif
     h->launches += 1;
@@ -252,6 +271,7 @@ struct ScoreArgs {
     const float *boxes, *dims, *pinv;
     const int32_t *orient;
     const u64 *pairs;
+    const int32_t *scan_index;       // plane index of every position of `pairs`
     const float4 *planes;
     int n_planes;
 };
@@ -289,13 +309,15 @@ __global__ void scores_fast_kernel(ScoreArgs a, int32_t *votes, float *resid, in
         // votes: fast count + 16 x the count that is possible within the margin (the VERIFIED filters' test);
         // zneg: fast z-check + 2 x "may pass the z-check within the margin"
         const f2 zhi = z_upper(h, D);
-        votes[2 * p] = V0 + 16 * loose_votes(h, false); resid[2 * p] = lo(R);
-        zneg[2 * p] = (lo(h.zc) < 0.0f ? 1 : 0) + (!(lo(zhi) < 0.0f) ? 2 : 0);
-        if (margin) margin[2 * p] = lo(h.m);
+        const int j0 = a.scan_index[2 * p];
+        votes[j0] = V0 + 16 * loose_votes(h, false); resid[j0] = lo(R);
+        zneg[j0] = (lo(h.zc) < 0.0f ? 1 : 0) + (!(lo(zhi) < 0.0f) ? 2 : 0);
+        if (margin) margin[j0] = lo(h.m);
         if (2 * p + 1 < a.n_planes) {
-            votes[2 * p + 1] = V1 + 16 * loose_votes(h, true); resid[2 * p + 1] = hi(R);
-            zneg[2 * p + 1] = (hi(h.zc) < 0.0f ? 1 : 0) + (!(hi(zhi) < 0.0f) ? 2 : 0);
-            if (margin) margin[2 * p + 1] = hi(h.m);
+            const int j1 = a.scan_index[2 * p + 1];
+            votes[j1] = V1 + 16 * loose_votes(h, true); resid[j1] = hi(R);
+            zneg[j1] = (hi(h.zc) < 0.0f ? 1 : 0) + (!(hi(zhi) < 0.0f) ? 2 : 0);
+            if (margin) margin[j1] = hi(h.m);
         }
     }
 }
@@ -319,11 +341,13 @@ __global__ void scores_bottom_kernel(ScoreArgs a, int32_t *votes, float *resid, 
                  r3 = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
         const f2 S3 = add2(add2(abs2(r1), abs2(r2)), abs2(r3));
         const f2 m1 = fma2(S3, bc(9.5367431640625e-07f), fma2(g.w, bc(D.ms), bc(D.mc)));
-        votes[2 * p] = 0; zneg[2 * p] = 0; resid[2 * p] = lo(S3);
-        if (margin) margin[2 * p] = lo(m1);
+        const int j0 = a.scan_index[2 * p];
+        votes[j0] = 0; zneg[j0] = 0; resid[j0] = lo(S3);
+        if (margin) margin[j0] = lo(m1);
         if (2 * p + 1 < a.n_planes) {
-            votes[2 * p + 1] = 0; zneg[2 * p + 1] = 0; resid[2 * p + 1] = hi(S3);
-            if (margin) margin[2 * p + 1] = hi(m1);
+            const int j1 = a.scan_index[2 * p + 1];
+            votes[j1] = 0; zneg[j1] = 0; resid[j1] = hi(S3);
+            if (margin) margin[j1] = hi(m1);
         }
     }
 }
@@ -333,7 +357,7 @@ int launch_scores(gpp_handle *h, const float *d_det /*12+3+12 floats*/, const in
     const int threads = 128, blocks = 64;
     ScoreArgs a;
     a.boxes = d_det; a.dims = d_det + 12; a.pinv = d_det + 15; a.orient = d_orient;
-    a.pairs = h->d_pairs; a.planes = h->d_planes32; a.n_planes = h->n_planes;
+    a.pairs = h->d_pairs; a.scan_index = h->d_scan_index; a.planes = h->d_planes32; a.n_planes = h->n_planes;
     if (which == 0) scores_exact_kernel<<<blocks, threads, 0, s>>>(a, votes, resid, zneg);
     else if (which == 1) scores_fast_kernel<false><<<blocks, threads, 0, s>>>(a, votes, resid, zneg, margin);
     else if (which == 2) scores_fast_kernel<true><<<blocks, threads, 0, s>>>(a, votes, resid, zneg, margin);

@@ -27,6 +27,23 @@
 #include "gpp_poll2.cuh"
 #include "gpp_pose.cuh"
 
+#ifdef GPP_NO_XLATE
+#define GPP_XLATE(p) (p)
+#else
+#define GPP_XLATE(p) __ldg(scan_index + (p))
+#endif
+#ifndef GPP_GENERAL_PREFETCH_EARLY
+#define GPP_GENERAL_PREFETCH_EARLY 1
+#endif
+#ifndef GPP_TD3_READBACK
+#define GPP_TD3_READBACK 1
+#endif
+#ifndef GPP_TWO_LOOPS
+#define GPP_TWO_LOOPS 1
+#endif
+#ifndef GPP_GEN_EXIT
+#define GPP_GEN_EXIT 0
+#endif
 #ifndef GPP_STAGE2
 #define GPP_STAGE2 1      /* 0: experiment -- stage-1 survivors of the all-six phase go straight to the exact queue */
 #endif
@@ -43,8 +60,10 @@ enum { kModeFast = 0, kModeVerified = 1, kModeExact = 2, kModeF64 = 3 };
 struct PollArgs3 {
     const float *boxes, *dims, *pinv;
     const int32_t *orient;
-    const u64 *pairs;            // pair-interleaved normalised fp32 DB, {a0,a1,b0,b1,c0,c1,d0,d1} per pair: FAST / VERIFIED
-    const float4 *planes;        // plain normalised fp32 DB: exact paths, EXACT scan
+    const u64 *pairs;            // pair-interleaved normalised fp32 DB, {a0,a1,b0,b1,c0,c1,d0,d1} per pair, in scan order: FAST / VERIFIED
+    const int32_t *scan_index;   // plane index of every position of `pairs` (gpp_order.cu)
+    const float4 *planes;        // plain normalised fp32 DB (index order): exact re-evaluation, epilogue
+    const float4 *planes_scan;   // the same in scan order: EXACT scan
     const double4 *planes64;     // fp64 DB: F64 scan
     int n_planes, n_pairs_padded, dets_per_image;
     long long n_det;
@@ -55,7 +74,9 @@ struct PollArgs3 {
     // schedule
     int det_stride;              // 1; n > 1 polls rows 0, n, 2n, ... only (runtime audit), without the repeated-row logic
     int resident_rows;           // rows of `pairs` kept in shared memory (0 = stream everything from L2)
-    int n_seg, rows_per_seg;     // plane segments per detection
+    int n_seg;                   // plane segments per detection: a segment takes the rows seg, seg + n_seg, ... of the scan
+                                 // order (rows of 64 planes for the packed scans, of 32 for the scalar ones), so every
+                                 // segment starts in the sample rows that order puts first
     unsigned long long *claim;   // [0] work-item counter, [1] CTAs that have left; zero at launch, reset by the last CTA
     SegPartial *partials;        // [n_det * n_seg]                      (n_seg > 1 only)
     unsigned int *seg_arrived;   // [n_det], zero at launch, reset by the last segment of the detection
@@ -110,12 +131,15 @@ struct RowSource {
     int res_left;              // resident rows from the current one on (<= 0: the current row is streamed)
     // constants
     uint32_t sbase;            // shared-memory address of the resident rows
+    uint32_t step_bytes;       // distance between two rows of the segment (1 KB x segments per detection)
     const unsigned char *gbase;   // global address of the pair database
-    __device__ __forceinline__ void init(uint32_t sbase_, const void *pairs, int res, int r_begin, int r_end, int lane) {
+    __device__ __forceinline__ void init(uint32_t sbase_, const void *pairs, int res, int r_begin, int step, int n_rows,
+                                         int lane) {
         sbase = sbase_;
         gbase = static_cast<const unsigned char *>(pairs);
         saddr = sbase_ + (uint32_t(r_begin) << 10) + 32u * lane;
-        rows_left = r_end - r_begin;
+        step_bytes = uint32_t(step) << 10;
+        rows_left = (n_rows - r_begin + step - 1) / step;
         res_left = res - r_begin;
     }
     __device__ __forceinline__ void load(bool resident, uint32_t addr, ulonglong2 &a, ulonglong2 &b) const {
@@ -129,14 +153,19 @@ struct RowSource {
         }
     }
     __device__ __forceinline__ bool more() const { return rows_left > 1; }
-    __device__ __forceinline__ void load_next(ulonglong2 &a, ulonglong2 &b) const { load(res_left > 1, saddr + 1024u, a, b); }
-    __device__ __forceinline__ void load_again(ulonglong2 &a, ulonglong2 &b) const { load(res_left > 0, saddr, a, b); }
-    __device__ __forceinline__ void advance() {
-        saddr += 1024u;
-        --rows_left;
-        --res_left;
+    template <bool kStep>
+    __device__ __forceinline__ void load_next(ulonglong2 &a, ulonglong2 &b) const {
+        if (kStep) load(res_left > int(step_bytes >> 10), saddr + step_bytes, a, b);
+        else load(res_left > 1, saddr + 1024u, a, b);
     }
-    __device__ __forceinline__ int plane_index() const { return int((saddr - sbase) >> 4); }   // first plane of the lane's pair
+    __device__ __forceinline__ void load_again(ulonglong2 &a, ulonglong2 &b) const { load(res_left > 0, saddr, a, b); }
+    template <bool kStep>
+    __device__ __forceinline__ void advance() {
+        saddr += kStep ? step_bytes : 1024u;
+        --rows_left;
+        res_left -= kStep ? int(step_bytes >> 10) : 1;
+    }
+    __device__ __forceinline__ int position() const { return int((saddr - sbase) >> 4); }   // of the first plane of the lane's pair
 };
 
 // ------------------------------------------------------------------ VERIFIED: filter + exact bookkeeping of a warp
@@ -145,17 +174,40 @@ struct RowSource {
 // certain planes, survivors queued and re-evaluated 32 at a time in the exact arithmetic.
 // development counters (-DGPP_STATS, printed by launch_poll3): [0] rows in the all-six phase, [1] of them past stage 1,
 // [2] rows in the general phase, [3] exact verifications, [4] flushes, [5] work items, [6] items polled in the
-// identical-rays form, [7] rows past the whole filter (something queued)
+// identical-rays form, [7] rows past the whole filter (something queued), [8] general-phase rows (max-votes >= 4) past
+// the bottom-face test, [9] general-phase rows at max-votes >= 4
 #ifdef GPP_STATS
-__device__ unsigned long long g_stats3[8];
+__device__ unsigned long long g_stats3[10];
 #define GPP_STAT3(i, n) (stat[i] += (n))
 #else
 #define GPP_STAT3(i, n) ((void)0)
 #endif
 
+// Exact re-evaluation of the warp's queue, out of line: ONE copy of the exact hypothesis for the three places that drain
+// the queue (the two scan loops and the end of a segment) instead of five inlined ones -- 15 KB less code for the 32
+// warps of a CTA to share the instruction cache with -- and none of its registers in the scan loops' allocation.  It
+// runs a few times per detection.  `n` entries starting at queue[first]; returns the lane's updated selection state.
+struct LaneSel {
+    int M;
+    float bestR;
+    int bestIdx;
+};
+static __device__ __noinline__ LaneSel verify_queue(const float *detx, const float4 *__restrict__ planes, const int *queue,
+                                             int first, int n, int lane, int M, float bestR, int bestIdx) {
+    const Detection<ExactF32> det = load_det_exact(detx);
+    LaneState<float> st;
+    st.M = M; st.bestR = bestR; st.bestIdx = bestIdx;
+#pragma unroll 1
+    for (int at = first; at < first + n; at += 32)
+        if (at + lane < first + n) verify_general(det, planes, queue[at + lane], st);
+    LaneSel out;
+    out.M = st.M; out.bestR = st.bestR; out.bestIdx = st.bestIdx;
+    return out;
+}
+
 struct VerifiedScan {
 #ifdef GPP_STATS
-    unsigned int stat[8];
+    unsigned int stat[10];
 #endif
     LaneState<float> st;   // exact selection state of this lane (max-votes, best residual, index)
     float wbest;           // warp-uniform: best EXACT residual so far at max-votes Mcur (or an early upper bound of it)
@@ -170,7 +222,7 @@ struct VerifiedScan {
         qn = 0;
         Mcur = -1;
 #ifdef GPP_STATS
-        for (int i = 0; i < 8; ++i) stat[i] = 0;
+        for (int i = 0; i < 10; ++i) stat[i] = 0;
         stat[5] = 1;
 #endif
     }
@@ -193,16 +245,14 @@ struct VerifiedScan {
 
     __device__ __forceinline__ void flush(const float *detx, const float4 *__restrict__ planes, const int *queue,
                                           int lane, bool all, const DetConst &D) {
-        const Detection<ExactF32> det = load_det_exact(detx);
         GPP_STAT3(4, 1);
         GPP_STAT3(3, all ? qn : (qn & ~31));
-        while (qn >= 32) {
-            qn -= 32;
-            verify_general(det, planes, queue[qn + lane], st);
-        }
-        if (all && qn > 0) {
-            if (lane < qn) verify_general(det, planes, queue[lane], st);
-            qn = 0;
+        {
+            // whole batches of 32 from the top of the queue; everything when a plane may raise max-votes
+            const int keep = all ? 0 : (qn & 31);
+            const LaneSel r = verify_queue(detx, planes, queue, keep, qn - keep, lane, st.M, st.bestR, st.bestIdx);
+            st.M = r.M; st.bestR = r.bestR; st.bestIdx = r.bestIdx;
+            qn = keep;
         }
         __syncwarp();
         const int Mnew = __reduce_max_sync(0xffffffffu, st.M);
@@ -216,136 +266,107 @@ struct VerifiedScan {
         wthr = (wbest + D.mc) * 1.0000038f;
     }
 
-    // One row: c0 / c1 hold this lane's pair of the current row on entry and of the next row (if any) on return.
-    // `Dh` carries the hot constants only (rays l, m, r, the bottom-face targets, the margin scale).
-    __device__ __forceinline__ void row(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
-                                        const int N, const int lane, int *queue, const float *detx,
-                                        const float4 *__restrict__ planes) {
-        DetConst D = Dh;
-        PairResult h;
-        bool trig0, trig1, urgent = false;
-        Bottom g;
-        eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
-        if (src.more()) src.load_next(c0, c1);
-        if (Mcur == 6) {
-            // stage 1: the bottom face only
-            GPP_STAT3(0, 1);
-            eval_bottom_rest<true, true>(D, g);
+    // A row of the general phase (max-votes so far below 6).  false: no plane of the row can matter.
+    __device__ __forceinline__ bool general_row(DetConst &D, const RowSource &src, Bottom &g, PairResult &h, bool &trig0,
+                                                bool &trig1, bool &urgent, const float *detx) {
+        GPP_STAT3(2, 1);
+        load_cold(D, detx);
+        eval_bottom_rest<false, true>(D, g);
+        if (GPP_GEN_EXIT && Mcur >= 4) {
+            // The bottom face alone: a plane has at most 3 + (bottom-face votes) votes, and its residual sum is at
+            // least S3.  It can have MORE votes than Mcur only if Mcur - 2 bottom residuals may be within 0.7, and AS
+            // MANY only if Mcur - 3 may be and S3 may stay below the best: order statistics of the three.  (Rows of
+            // similar planes -- gpp_order.cu -- mostly fail together; detections without a six-vote plane spend their
+            // whole scan here.)  m1 bounds |fast - exact| of each of the three and of their sum (stage 1).
+            const f2 a1 = abs2(sub2(PackFast::sqrt(g.na), bc(D.td[1]))), a2 = abs2(sub2(PackFast::sqrt(g.nb), bc(D.td[2]))),
+                     a3 = abs2(sub2(PackFast::sqrt(g.nc), bc(D.td[3])));
+            const f2 S3 = add2(add2(a1, a2), a3);
+            const f2 m1 = fma2(S3, bc(9.5367431640625e-07f), fma2(g.w, bc(D.ms), bc(D.mc)));
+            const float md0 = fmaxf(fminf(lo(a1), lo(a2)), fminf(fmaxf(lo(a1), lo(a2)), lo(a3)));
+            const float md1 = fmaxf(fminf(hi(a1), hi(a2)), fminf(fmaxf(hi(a1), hi(a2)), hi(a3)));
+            float more0, more1, same0, same1;
+            if (Mcur == 5) {
+                more0 = max3f(lo(a1), lo(a2), lo(a3)); more1 = max3f(hi(a1), hi(a2), hi(a3));
+                same0 = md0; same1 = md1;
+            } else {
+                more0 = md0; more1 = md1;
+                same0 = fminf(fminf(lo(a1), lo(a2)), lo(a3)); same1 = fminf(fminf(hi(a1), hi(a2)), hi(a3));
+            }
+            const f2 Slo = sub2(S3, m1);
+            const bool nan0 = !(lo(S3) == lo(S3)), nan1 = !(hi(S3) == hi(S3));      // degenerate: full test
+            const bool may0 = nan0 || !(more0 - lo(m1) > 0.7f) || (!(same0 - lo(m1) > 0.7f) && !(lo(Slo) > wbest));
+            const bool may1 = nan1 || !(more1 - hi(m1) > 0.7f) || (!(same1 - hi(m1) > 0.7f) && !(hi(Slo) > wbest));
+            GPP_STAT3(9, 1);
+            if (!__any_sync(0xffffffffu, may0 || may1)) return false;
+            GPP_STAT3(8, 1);
+            // The rows that go on form the three residuals again after eval_top (nine instructions for the 4 % of the
+            // rows that get here): kept across it, they are what pushes the kernel past 64 registers.
+            asm volatile("" : "+l"(g.na.v), "+l"(g.nb.v), "+l"(g.nc.v));
+        }
+        {
+            ulonglong2 v0, v1;
+            src.load_again(v0, v1);
+            f2 ne, nf;
+            eval_top<1, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), g, h, ne, nf);
             h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
             h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
             h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
-            const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
-            const f2 Slo = fma2(neg2(g.w), bc(D.ms), S3);
-            if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) return;
-#if !GPP_STAGE2
-            // experiment (measured r02: 1595 exact verifications per detection instead of 79, 3.8e11 instead of 4.8e11
-            // hypotheses/s -- the second stage is what keeps the exact path rare)
-            GPP_STAT3(1, 1);
-            trig0 = !(lo(Slo) > wthr);
-            trig1 = !(hi(Slo) > wthr);
-#else
-            // stage 2: X_t, the height and the two slanted edges, the full margin
-            GPP_STAT3(1, 1);
-            load_cold(D, detx);
-            ulonglong2 v0, v1;
-            src.load_again(v0, v1);
-            const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
-            f2 ne, nf;
-            eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
             h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
             h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
-            const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
-            const f2 Rlo = sub2(R, h.m);
-            trig0 = !(lo(Rlo) > wthr);
-            trig1 = !(hi(Rlo) > wthr);
-            if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
-            h.m = add2(h.m, bc(D.mc));
-            finalize_margin(h, R, D);
-            const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
-                             rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
-            const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
-            trig0 = trig0 && !(lo(rlo) > 0.7f);
-            trig1 = trig1 && !(hi(rlo) > 0.7f);
-            if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
-            h.finish_zc();
-            const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
-            const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
-            {
-                // a plane that CERTAINLY has six votes and passes the z-check bounds the final best residual
-                const f2 Rhi = fma2(R, bc(1.000001f), h.m);
-                const f2 rhi = add2(rm, h.m);
-                const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
-                const float e0 = (lo(rhi) <= 0.7f && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX) ? lo(Rhi) : FLT_MAX;
-                const float e1 = (hi(rhi) <= 0.7f && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX) ? hi(Rhi) : FLT_MAX;
-                const float e = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(e0, e1))));
-                if (e < wbest) {
-                    wbest = e;
-                    wthr = (wbest + D.mc) * 1.0000038f;
-                }
-            }
-            trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
-            trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
-#endif
-        } else {
-            GPP_STAT3(2, 1);
-            load_cold(D, detx);
-            eval_bottom_rest<false, true>(D, g);
-            {
-                ulonglong2 v0, v1;
-                src.load_again(v0, v1);
-                f2 ne, nf;
-                eval_top<1, true>(D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), g, h, ne, nf);
-                h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
-                h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
-                h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
-                h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
-                h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
-            }
-            const f2 R = resid_sum(h);
-            finalize_margin(h, R, D);
-            const f2 Rlo = sub2(R, h.m);
-            if (Mcur >= 4) {
-                const f2 p0 = pk(fmaxf(fabsf(lo(h.r[0])), fabsf(lo(h.r[1]))), fmaxf(fabsf(hi(h.r[0])), fabsf(hi(h.r[1]))));
-                const f2 p1 = pk(fmaxf(fabsf(lo(h.r[2])), fabsf(lo(h.r[3]))), fmaxf(fabsf(hi(h.r[2])), fabsf(hi(h.r[3]))));
-                const f2 p2 = pk(fmaxf(fabsf(lo(h.r[4])), fabsf(lo(h.r[5]))), fmaxf(fabsf(hi(h.r[4])), fabsf(hi(h.r[5]))));
-                const f2 pmax = pk(max3f(lo(p0), lo(p1), lo(p2)), max3f(hi(p0), hi(p1), hi(p2)));
-                const f2 pmin = pk(fminf(fminf(lo(p0), lo(p1)), lo(p2)), fminf(fminf(hi(p0), hi(p1)), hi(p2)));
-                const f2 pmed = pk(fmaxf(fminf(lo(p0), lo(p1)), fminf(fmaxf(lo(p0), lo(p1)), lo(p2))),
-                                   fmaxf(fminf(hi(p0), hi(p1)), fminf(fmaxf(hi(p0), hi(p1)), hi(p2))));
-                const f2 more = sub2(Mcur == 5 ? pmax : pmed, h.m);      // > 0.7: cannot have more votes
-                const f2 same = sub2(Mcur == 5 ? pmed : pmin, h.m);      // > 0.7: cannot have as many
-                const bool nan0 = !(lo(R) == lo(R)), nan1 = !(hi(R) == hi(R));   // degenerate: full test
-                const bool may0 = nan0 || !(lo(more) > 0.7f) || (!(lo(same) > 0.7f) && !(lo(Rlo) > wbest));
-                const bool may1 = nan1 || !(hi(more) > 0.7f) || (!(hi(same) > 0.7f) && !(hi(Rlo) > wbest));
-                if (!__any_sync(0xffffffffu, may0 || may1)) return;
-            }
-            h.finish_zc();
-            const f2 zhi = z_upper(h, D);
-            const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
-            const bool k0 = V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
-            const bool k1 = V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
-            if (Mcur >= 4 && __any_sync(0xffffffffu, k0 || k1)) {
-                const f2 Rhi = fma2(R, bc(1.000001f), h.m);
-                const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
-                const bool c0 = k0 && strict_votes(h, false) == Mcur && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX;
-                const bool c1 = k1 && strict_votes(h, true) == Mcur && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX;
-                const float e = __uint_as_float(__reduce_min_sync(
-                    0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
-                wbest = fminf(wbest, e);
-            }
-            trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
-            trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
-            urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
         }
-        const int j = src.plane_index();
-        const bool q0 = trig0 && (j < N), q1 = trig1 && (j + 1 < N);
+        const f2 R = resid_sum(h);
+        finalize_margin(h, R, D);
+        const f2 Rlo = sub2(R, h.m);
+        if (Mcur >= 4) {
+            const f2 p0 = pk(fmaxf(fabsf(lo(h.r[0])), fabsf(lo(h.r[1]))), fmaxf(fabsf(hi(h.r[0])), fabsf(hi(h.r[1]))));
+            const f2 p1 = pk(fmaxf(fabsf(lo(h.r[2])), fabsf(lo(h.r[3]))), fmaxf(fabsf(hi(h.r[2])), fabsf(hi(h.r[3]))));
+            const f2 p2 = pk(fmaxf(fabsf(lo(h.r[4])), fabsf(lo(h.r[5]))), fmaxf(fabsf(hi(h.r[4])), fabsf(hi(h.r[5]))));
+            const f2 pmax = pk(max3f(lo(p0), lo(p1), lo(p2)), max3f(hi(p0), hi(p1), hi(p2)));
+            const f2 pmin = pk(fminf(fminf(lo(p0), lo(p1)), lo(p2)), fminf(fminf(hi(p0), hi(p1)), hi(p2)));
+            const f2 pmed = pk(fmaxf(fminf(lo(p0), lo(p1)), fminf(fmaxf(lo(p0), lo(p1)), lo(p2))),
+                               fmaxf(fminf(hi(p0), hi(p1)), fminf(fmaxf(hi(p0), hi(p1)), hi(p2))));
+            const f2 more = sub2(Mcur == 5 ? pmax : pmed, h.m);      // > 0.7: cannot have more votes
+            const f2 same = sub2(Mcur == 5 ? pmed : pmin, h.m);      // > 0.7: cannot have as many
+            const bool nan0 = !(lo(R) == lo(R)), nan1 = !(hi(R) == hi(R));   // degenerate: full test
+            const bool may0 = nan0 || !(lo(more) > 0.7f) || (!(lo(same) > 0.7f) && !(lo(Rlo) > wbest));
+            const bool may1 = nan1 || !(hi(more) > 0.7f) || (!(hi(same) > 0.7f) && !(hi(Rlo) > wbest));
+            if (!__any_sync(0xffffffffu, may0 || may1)) return false;
+        }
+        h.finish_zc();
+        const f2 zhi = z_upper(h, D);
+        const int V0 = loose_votes(h, false), V1 = loose_votes(h, true);
+        const bool k0 = V0 == Mcur && !(lo(zhi) < 0.0f) && !(lo(Rlo) > wbest);
+        const bool k1 = V1 == Mcur && !(hi(zhi) < 0.0f) && !(hi(Rlo) > wbest);
+        if (Mcur >= 4 && __any_sync(0xffffffffu, k0 || k1)) {
+            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+            const bool c0 = k0 && strict_votes(h, false) == Mcur && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX;
+            const bool c1 = k1 && strict_votes(h, true) == Mcur && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX;
+            const float e = __uint_as_float(__reduce_min_sync(
+                0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
+            wbest = fminf(wbest, e);
+        }
+        trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
+        trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
+        urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
+        return true;
+    }
+
+    // survivors of a row -> the warp's queue (plane indices); a full batch, or a plane that may raise max-votes, is
+    // verified at once
+    __device__ __forceinline__ void enqueue(bool trig0, bool trig1, bool urgent, const RowSource &src, const int N,
+                                            const int lane, int *queue, const float *detx,
+                                            const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index,
+                                            const DetConst &D) {
+        const int pos = src.position();
+        const bool q0 = trig0 && (pos < N), q1 = trig1 && (pos + 1 < N);
         const unsigned b0 = __ballot_sync(0xffffffffu, q0), b1 = __ballot_sync(0xffffffffu, q1);
         if (b0 | b1) {
             GPP_STAT3(7, 1);
             const unsigned below = (1u << lane) - 1u;
-            if (q0) queue[qn + __popc(b0 & below)] = j;
+            if (q0) queue[qn + __popc(b0 & below)] = GPP_XLATE(pos);       // the queue holds plane indices
             qn += __popc(b0);
-            if (q1) queue[qn + __popc(b1 & below)] = j + 1;
+            if (q1) queue[qn + __popc(b1 & below)] = GPP_XLATE(pos + 1);
             qn += __popc(b1);
             __syncwarp();
             const bool flush_all = __any_sync(0xffffffffu, urgent);
@@ -353,19 +374,124 @@ struct VerifiedScan {
         }
     }
 
+    // The scan of a segment is two loops (the kernel below): rows are polled by row_general until the exact max-votes
+    // reaches 6 -- it never falls again -- and by row_six from then on, so that the hot loop carries nothing of the
+    // general phase.  In both, c0 / c1 hold this lane's pair of the current row on entry and of the next row (if any)
+    // on return; `Dh` carries the hot constants only (rays l, m, r, the bottom-face targets, the margin scale).
+    template <bool kStep>
+    __device__ __forceinline__ void row_general(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+                                                const int N, const int lane, int *queue, const float *detx,
+                                                const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index) {
+        DetConst D = Dh;
+        PairResult h;
+        bool trig0, trig1, urgent = false;
+        Bottom g;
+        eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
+#if GPP_GENERAL_PREFETCH_EARLY
+        if (src.more()) src.load_next<kStep>(c0, c1);
+        if (!general_row(D, src, g, h, trig0, trig1, urgent, detx)) return;
+#else
+        // the next row is fetched once the row's registers are free again
+        const bool keep = general_row(D, src, g, h, trig0, trig1, urgent, detx);
+        if (src.more()) src.load_next<kStep>(c0, c1);
+        if (!keep) return;
+#endif
+        enqueue(trig0, trig1, urgent, src, N, lane, queue, detx, planes, scan_index, D);
+    }
+
+    template <bool kStep>
+    __device__ __forceinline__ void row_six(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+                                            const int N, const int lane, int *queue, const float *detx,
+                                            const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index) {
+        DetConst D = Dh;
+        PairResult h;
+        bool trig0, trig1;
+        Bottom g;
+        eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
+        if (src.more()) src.load_next<kStep>(c0, c1);
+        // stage 1: the bottom face only
+        if (src.more()) src.load_next<kStep>(c0, c1);
+        GPP_STAT3(0, 1);
+        eval_bottom_rest<true, true>(D, g);
+        h.r[1] = sub2(PackFast::sqrt(g.na), bc(D.td[1]));
+        h.r[2] = sub2(PackFast::sqrt(g.nb), bc(D.td[2]));
+        h.r[3] = sub2(PackFast::sqrt(g.nc), bc(D.td[3]));
+        const f2 S3 = add2(add2(abs2(h.r[1]), abs2(h.r[2])), abs2(h.r[3]));
+        const f2 Slo = fma2(neg2(g.w), bc(D.ms), S3);
+        if (!__any_sync(0xffffffffu, !(lo(Slo) > wthr) || !(hi(Slo) > wthr))) return;
+#if !GPP_STAGE2
+        // experiment (measured r02: 1595 exact verifications per detection instead of 79, 3.8e11 instead of 4.8e11
+        // hypotheses/s -- the second stage is what keeps the exact path rare)
+        GPP_STAT3(1, 1);
+        trig0 = !(lo(Slo) > wthr);
+        trig1 = !(hi(Slo) > wthr);
+#else
+        // stage 2: X_t, the height and the two slanted edges, the full margin
+        GPP_STAT3(1, 1);
+        load_cold(D, detx);
+        ulonglong2 v0, v1;
+        src.load_again(v0, v1);
+        const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
+        f2 ne, nf;
+        eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+        h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
+        h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
+        const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
+        const f2 Rlo = sub2(R, h.m);
+        trig0 = !(lo(Rlo) > wthr);
+        trig1 = !(hi(Rlo) > wthr);
+        if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
+        h.m = add2(h.m, bc(D.mc));
+        finalize_margin(h, R, D);
+        const f2 rm = pk(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])),
+                         rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])));
+        const f2 rlo = sub2(rm, h.m);               // lower bound of max |r_k|
+        trig0 = trig0 && !(lo(rlo) > 0.7f);
+        trig1 = trig1 && !(hi(rlo) > 0.7f);
+        if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
+        h.finish_zc();
+        const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
+        const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
+        {
+            // a plane that CERTAINLY has six votes and passes the z-check bounds the final best residual
+            const f2 Rhi = fma2(R, bc(1.000001f), h.m);
+            const f2 rhi = add2(rm, h.m);
+            const f2 zlo = fma2(h.zc, bc(2.0f), neg2(zhi));
+            const float e0 = (lo(rhi) <= 0.7f && lo(zlo) > 0.0f && lo(Rhi) < FLT_MAX) ? lo(Rhi) : FLT_MAX;
+            const float e1 = (hi(rhi) <= 0.7f && hi(zlo) > 0.0f && hi(Rhi) < FLT_MAX) ? hi(Rhi) : FLT_MAX;
+            const float e = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(e0, e1))));
+            if (e < wbest) {
+                wbest = e;
+                wthr = (wbest + D.mc) * 1.0000038f;
+            }
+        }
+        trig0 = !(lo(Rl2) > wbest) && !(lo(rlo) > 0.7f) && !(lo(zhi) < 0.0f);
+        trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
+#endif
+        enqueue(trig0, trig1, false, src, N, lane, queue, detx, planes, scan_index, D);
+    }
+
+    template <bool kStep>
+    __device__ __forceinline__ void row(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+                                        const int N, const int lane, int *queue, const float *detx,
+                                        const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index) {
+        if (Mcur == 6) row_six<kStep>(Dh, src, c0, c1, N, lane, queue, detx, planes, scan_index);
+        else row_general<kStep>(Dh, src, c0, c1, N, lane, queue, detx, planes, scan_index);
+    }
+
     // end of the segment: the last partial batch; afterwards `st` holds the exact result of the scanned planes
     __device__ __forceinline__ void finish(const float *detx, const float4 *__restrict__ planes, const int *queue,
                                            int lane) {
         if (qn > 0) {
-            const Detection<ExactF32> det = load_det_exact(detx);
             GPP_STAT3(3, qn);
-            if (lane < qn) verify_general(det, planes, queue[lane], st);
+            const LaneSel r = verify_queue(detx, planes, queue, 0, qn, lane, st.M, st.bestR, st.bestIdx);
+            st.M = r.M; st.bestR = r.bestR; st.bestIdx = r.bestIdx;
             qn = 0;
             __syncwarp();
         }
 #ifdef GPP_STATS
         if (lane == 0)
-            for (int i = 0; i < 8; ++i) atomicAdd(&g_stats3[i], (unsigned long long)stat[i]);
+            for (int i = 0; i < 10; ++i) atomicAdd(&g_stats3[i], (unsigned long long)stat[i]);
 #endif
     }
     __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx) const {
@@ -389,12 +515,18 @@ struct FastScan {
         m6 = false;
         wbest = FLT_MAX;
     }
-    __device__ __forceinline__ void row(const DetConst &D, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1) {
+    // The state holds POSITIONS of the scan order; equal residuals (duplicate planes) are settled by the plane index.
+    static __device__ __forceinline__ bool index_below(const int32_t *__restrict__ scan_index, int pos, int other) {
+        return __ldg(scan_index + pos) < __ldg(scan_index + other);
+    }
+    template <bool kStep>
+    __device__ __forceinline__ void row(const DetConst &D, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
+                                        const int32_t *__restrict__ scan_index) {
         PairResult h;
-        const int j = src.plane_index();
+        const int j = src.position();
         Bottom g;
         eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
-        if (src.more()) src.load_next(c0, c1);
+        if (src.more()) src.load_next<kStep>(c0, c1);
         if (!m6) {
             eval_bottom_rest<false, false>(D, g);
             {
@@ -411,8 +543,8 @@ struct FastScan {
             const f2 R = resid_sum(h);
             const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
             const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
-            st.update(V0, lo(R), lo(h.zc) < 0.0f, j, FLT_MAX);
-            st.update(V1, hi(R), hi(h.zc) < 0.0f, j + 1, FLT_MAX);
+            update_general(V0, lo(R), lo(h.zc) < 0.0f, j, scan_index);
+            update_general(V1, hi(R), hi(h.zc) < 0.0f, j + 1, scan_index);
             if ((src.rows_left & 3) == 0 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
                 m6 = true;                               // warp-uniform; candidates under a lower max are masked
                 b6.bestR = (st.M == 6) ? st.bestR : FLT_MAX;
@@ -441,20 +573,38 @@ struct FastScan {
         const f2 R = resid_sum(h);
         if (__any_sync(0xffffffffu, !(lo(R) > wbest) || !(hi(R) > wbest))) {
             h.finish_zc();
-            b6.update6(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])), lo(h.zc), lo(R), j);
-            b6.update6(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])), hi(h.zc), hi(R), j + 1);
+            update_six(rmax_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5])), lo(h.zc), lo(R), j, scan_index);
+            update_six(rmax_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5])), hi(h.zc), hi(R), j + 1, scan_index);
             wbest = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(b6.bestR)));
         }
     }
-    __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx) const {
+    // LaneState::update / LaneBest::update6 for a scan that does not visit the planes in index order
+    __device__ __forceinline__ void update_general(int V, float R, bool zneg, int pos, const int32_t *__restrict__ scan_index) {
+        const bool grow = V > st.M;
+        const float cur = grow ? FLT_MAX : st.bestR;
+        bool better = (V >= st.M) && !zneg && (R < cur);
+        if ((V >= st.M) && !zneg && R == cur && R < FLT_MAX) better = index_below(scan_index, pos, st.bestIdx);
+        st.bestR = better ? R : cur;
+        st.bestIdx = better ? pos : st.bestIdx;
+        st.M = max(st.M, V);
+    }
+    __device__ __forceinline__ void update_six(float rmax, float zc, float R, int pos, const int32_t *__restrict__ scan_index) {
+        const bool ok = !(rmax > 0.7f) && !(zc < 0.0f);
+        bool better = ok && (R < b6.bestR);
+        if (ok && R == b6.bestR && R < FLT_MAX) better = index_below(scan_index, pos, b6.bestIdx);
+        b6.bestR = better ? R : b6.bestR;
+        b6.bestIdx = better ? pos : b6.bestIdx;
+    }
+    // the lane's best as (max-votes, residual, PLANE INDEX)
+    __device__ __forceinline__ void result(int &Mw, float &rbest, int &idx, const int32_t *__restrict__ scan_index) const {
         if (m6) {
             Mw = 6;
             rbest = b6.bestR;
-            idx = b6.bestIdx;
+            idx = __ldg(scan_index + b6.bestIdx);
         } else {
             Mw = __reduce_max_sync(0xffffffffu, st.M);
             rbest = (st.M == Mw) ? st.bestR : FLT_MAX;
-            idx = st.bestIdx;
+            idx = __ldg(scan_index + st.bestIdx);
         }
     }
 };
@@ -481,59 +631,76 @@ __host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
 }
 
 // ------------------------------------------------------------------ EXACT / F64: scalar scan, one plane per lane
-// The hypothesis comes in two halves (gpp_math.cuh): once a plane with six votes is known, a plane matters only if its
-// residual sum does not exceed the warp's best six-vote residual.  No partial sum of the residuals exceeds the full
-// sum (rounded addition of non-negative terms is monotone; a NaN / inf sum never wins), so the hypothesis is built in
-// steps and dropped as soon as all 32 lanes are out: r3 > best after the points l and r (two of the four divisions,
-// one of the six square roots), (r1 + r2) + r3 > best after the point m; X_t, the last division and three square
-// roots are reached by about one row in four.  Nothing that is kept changes by a bit.
+// The hypothesis comes in steps (gpp_math.cuh).  Once the warp's max-votes M is 5 or 6, a plane matters only if it can
+// have more votes than M -- impossible at 6; at 5 all three bottom-face residuals would have to vote -- or as many and a
+// residual sum that does not exceed the warp's best at M.  No partial sum of the residuals exceeds the full sum (rounded
+// addition of non-negative terms is monotone; a NaN / inf sum never wins, a NaN residual votes and keeps the plane), so
+// the hypothesis is dropped as soon as all 32 lanes are out: r3 > best after the points l and r (two of the four
+// divisions, one of the six square roots; the diagonal is the longest edge), (r1 + r2) + r3 > best after the point m.
+// Nothing that is kept changes by a bit.  The planes come in scan order (gpp_order.cu: rows of similar planes leave
+// together, a sample of the whole database first); `index` maps a position back to the plane index, which settles equal
+// residuals (null: index order, the F64 database).  A segment takes the rows of 32 planes first, first + step, ...
+template <class T>
+__device__ __forceinline__ void update_unordered(LaneState<T> &st, int V, T R, bool zneg, int j, T highest) {
+    const bool grow = V > st.M;
+    const T cur = grow ? highest : st.bestR;
+    const bool better = (V >= st.M) && !zneg && (R < cur || (R == cur && R < highest && j < st.bestIdx));
+    st.bestR = better ? R : cur;
+    st.bestIdx = better ? j : st.bestIdx;
+    st.M = max(st.M, V);
+}
+
 template <class P>
 __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typename P::T4 *__restrict__ planes,
-                                            const int p_begin, const int p_end, const int lane, const bool same_rays,
+                                            const int32_t *__restrict__ index, const int first_row, const int row_step,
+                                            const int n_planes, const int lane, const bool same_rays,
                                             LaneState<typename P::T> &st) {
     typedef typename P::T T;
     typedef typename P::T4 T4;
     const T highest = P::highest();
+    const T thr = P::thresh();
     st.reset(highest);
     if (same_rays) {
         // FilterDetections' padding rows: the cheap form that identical rays allow (bit-identical, gpp_math.cuh)
 #pragma unroll 2
-        for (int j = p_begin + lane; j < p_end; j += 32) {
-            const T4 pl = planes[j];
+        for (int p = (first_row << 5) + lane; p < n_planes; p += row_step << 5) {
+            const T4 pl = planes[p];
             T X[4][3];
             int V; T R; bool z;
             hypothesis_same_rays<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
-            st.update(V, R, z, j, highest);
+            update_unordered(st, V, R, z, index ? __ldg(index + p) : p, highest);
         }
         return;
     }
-    bool m6 = false;
-    T wbest = highest;
+    int Mw = -1;                    // warp-uniform: max-votes so far (refreshed every fourth row while below 6)
+    T wbest = highest;              // best residual at Mw so far
     int it = 0;
 #pragma unroll 1
-    for (int j0 = p_begin; j0 < p_end; j0 += 32, ++it) {
-        const int j = j0 + lane;
-        const bool valid = j < p_end;                      // lanes past the end poll the last plane again and drop it
-        const T4 pl = planes[valid ? j : p_end - 1];
+    for (int p0 = first_row << 5; p0 < n_planes; p0 += row_step << 5, ++it) {
+        const int p = p0 + lane;
+        const bool valid = p < n_planes;                   // lanes past the end poll the last plane again and drop it
+        const T4 pl = planes[valid ? p : n_planes - 1];
         T X[4][3];
         int V; T R; bool zneg;
-        if (m6) {
+        if (Mw >= 5) {
             T rb[3];
             rb[2] = bottom_lr<P>(det, pl.x, pl.y, pl.z, pl.w, X);
-            if (!__any_sync(0xffffffffu, valid && !(rb[2] > wbest))) continue;
+            if (!__any_sync(0xffffffffu, valid && (!(rb[2] > wbest) || (Mw == 5 && !(rb[2] > thr))))) continue;
             bottom_m<P>(det, pl.x, pl.y, pl.z, pl.w, X, rb);
             const T S3 = P::add(P::add(rb[0], rb[1]), rb[2]);
-            if (!__any_sync(0xffffffffu, valid && !(S3 > wbest))) continue;
+            const bool all3 = !(rb[0] > thr) && !(rb[1] > thr) && !(rb[2] > thr);
+            if (!__any_sync(0xffffffffu, valid && (!(S3 > wbest) || (Mw == 5 && all3)))) continue;
             zneg = bottom_zneg<P>(X);
             hypothesis_top<P>(det, pl.x, pl.y, pl.z, X, rb, V, R);
-            if (valid) st.update(V, R, zneg, j, highest);
-            wbest = warp_min_value(st.M == 6 ? st.bestR : highest);
+            if (valid) update_unordered(st, V, R, zneg, index ? __ldg(index + p) : p, highest);
+            Mw = __reduce_max_sync(0xffffffffu, st.M);
+            wbest = warp_min_value(st.M == Mw ? st.bestR : highest);
         } else {
             hypothesis<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
-            if (valid) st.update(V, R, zneg, j, highest);
-            if ((it & 3) == 3 && __reduce_max_sync(0xffffffffu, st.M) == 6) {
-                m6 = true;
-                wbest = warp_min_value(st.M == 6 ? st.bestR : highest);
+            if (valid) update_unordered(st, V, R, zneg, index ? __ldg(index + p) : p, highest);
+            if ((it & 3) == 3) {
+                Mw = __reduce_max_sync(0xffffffffu, st.M);
+                wbest = warp_min_value(st.M == Mw ? st.bestR : highest);
             }
         }
     }
@@ -621,10 +788,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 store_cold(detx, D);
             }
             __syncwarp();
+#if GPP_TD3_READBACK
+            // td[3] comes out of an IEEE square root (a subroutine call the compiler cannot see through): read back from
+            // the warp's slot it is a load from a warp-uniform address, and joins the other hot constants in a uniform
+            // register instead of being reloaded from local memory on every row
+            D.td[3] = detx[15];
+#endif
         }
 
-        const int r_begin = kSeg ? seg * args.rows_per_seg : 0;
-        const int r_end = kSeg ? min(NR, r_begin + args.rows_per_seg) : NR;
         int Mw, idx;
         T rbest;
         if (!kPacked || (kVerified && same_rays)) {
@@ -633,7 +804,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             Detection<P> det;
             if constexpr (kPacked) det = load_det_exact(detx); else det = detE;
             LaneState<T> st;
-            scalar_scan<P>(det, planesT, r_begin << 6, min(N, r_end << 6), lane, same_rays, st);
+            if constexpr (kMode == kModeF64)
+                scalar_scan<P>(det, planesT, nullptr, seg, n_seg, N, lane, same_rays, st);
+            else
+                scalar_scan<P>(det, reinterpret_cast<const T4 *>(args.planes_scan), args.scan_index, seg, n_seg, N, lane,
+                               same_rays, st);
             Mw = __reduce_max_sync(0xffffffffu, st.M);
             rbest = (st.M == Mw) ? st.bestR : P::highest();
             idx = st.bestIdx;
@@ -641,8 +816,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             if (kVerified && lane == 0) { atomicAdd(&g_stats3[5], 1ull); atomicAdd(&g_stats3[6], 1ull); }
 #endif
         } else if constexpr (kPacked) {
+            // rows seg, seg + n_seg, ... of the pair database (scan order: gpp_order.cu)
             RowSource src;
-            src.init(smem_u32(smem_raw), args.pairs, res, r_begin, r_end, lane);
+            src.init(smem_u32(smem_raw), args.pairs, res, seg, n_seg, NR, lane);
             ulonglong2 c0, c1;
             src.load_again(c0, c1);
             float rb;
@@ -652,21 +828,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 // segments of one detection share their bounds: every fourth row a warp publishes its own (one atomicMax
                 // on the detection's 64-bit key) and adopts the best published so far (one uniform branch per row; the
                 // round-2 profile of C3 showed the per-row form of this exchange at 40 instructions a row)
-                for (; src.rows_left > 0; src.advance()) {
-                    sc.row(D, src, c0, c1, N, lane, queue, detx, args.planes);
+                auto exchange = [&]() {
                     if (kSeg && (src.rows_left & 3) == 1) {
                         unsigned long long key = seg_key(sc.Mcur, sc.wbest);
                         if (lane == 0) key = max(key, atomicMax(args.seg_best + slot, key));
                         sc.adopt(__shfl_sync(0xffffffffu, key, 0), detx);
                     }
+                };
+#if GPP_TWO_LOOPS
+                for (; src.rows_left > 0 && sc.Mcur < 6; src.advance<kSeg>()) {
+                    sc.row_general<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
+                    exchange();
                 }
+                for (; src.rows_left > 0; src.advance<kSeg>()) {
+                    sc.row_six<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
+                    exchange();
+                }
+#else
+                for (; src.rows_left > 0; src.advance<kSeg>()) {
+                    sc.row<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
+                    exchange();
+                }
+#endif
                 sc.finish(detx, args.planes, queue, lane);
                 sc.result(Mw, rb, idx);
             } else {
                 FastScan sc;
                 sc.begin();
-                for (; src.rows_left > 0; src.advance()) sc.row(D, src, c0, c1);
-                sc.result(Mw, rb, idx);
+                for (; src.rows_left > 0; src.advance<kSeg>()) sc.row<kSeg>(D, src, c0, c1, args.scan_index);
+                sc.result(Mw, rb, idx, args.scan_index);
             }
             rbest = rb;
         }
@@ -710,11 +900,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             int first_masked = -1;
             if constexpr (kMode == kModeFast) {
                 for (int p0 = 0; 2 * p0 < N && first_masked < 0; p0 += 32) {
-                    const int p = p0 + lane;                         // pair index; the padded DB covers it
-                    const ulonglong2 v0 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p);
-                    const ulonglong2 v1 = __ldg(reinterpret_cast<const ulonglong2 *>(args.pairs) + 2 * p + 1);
+                    const int p = p0 + lane;                         // planes (2p, 2p + 1) in INDEX order
+                    const float4 pa = __ldg(args.planes + min(2 * p, N - 1)), pb = __ldg(args.planes + min(2 * p + 1, N - 1));
                     PairResult h;
-                    eval_pair<false>(PackFast(), D, from_u64(v0.x), from_u64(v0.y), from_u64(v1.x), from_u64(v1.y), h);
+                    eval_pair<false>(PackFast(), D, pk(pa.x, pb.x), pk(pa.y, pb.y), pk(pa.z, pb.z), pk(pa.w, pb.w), h);
                     const int V0 = votes_of(lo(h.r[0]), lo(h.r[1]), lo(h.r[2]), lo(h.r[3]), lo(h.r[4]), lo(h.r[5]));
                     const int V1 = votes_of(hi(h.r[0]), hi(h.r[1]), hi(h.r[2]), hi(h.r[3]), hi(h.r[4]), hi(h.r[5]));
                     const bool mk0 = (2 * p < N) && ((V0 < Mw) || lo(h.zc) < 0.0f);

@@ -285,6 +285,15 @@ _POLLERS = {}
 _POLLERS_LOCK = threading.Lock()
 
 
+def scan_order(planes):
+    """The order in which the FAST / VERIFIED scans visit a database (csrc/gpp_order.cu): ``order[position] = plane
+    index``.  Host code of libgpp, needs no device; ``planes``: (N, 4) as fed (float32 after the Keras cast)."""
+    rows = np.ascontiguousarray(np.asarray(planes).reshape(-1, 4), dtype=np.float32)
+    order = np.empty(rows.shape[0], np.int32)
+    _lib.check(_lib.load().gpp_debug_scan_order(_lib.ptr(rows), rows.shape[0], _lib.ptr(order)), 'gpp_debug_scan_order')
+    return order
+
+
 def default_device():
     """LOCAL_RANK (one process per GPU under torchrun) or GPP_DEVICE, else 0."""
     for var in ('GPP_DEVICE', 'LOCAL_RANK'):

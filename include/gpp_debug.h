@@ -37,6 +37,11 @@ int gpp_debug_scores(gpp_handle *h, const float *box12, const float *dims3, int 
  * stream everything from L2).  Tests force the segmented and the streamed paths. */
 int gpp_debug_set_schedule(gpp_handle *h, int n_seg, int resident_rows);
 
+/* The order in which the FAST / VERIFIED scans visit a database (csrc/gpp_order.cu): order[position] = plane index,
+ * a permutation of 0 .. n_planes-1 (the identity below 32 rows of 64 planes).  `planes`: n_planes x 4 float32,
+ * row-major, as fed.  Host code only -- needs no device. */
+int gpp_debug_scan_order(const float *planes, int n_planes, int32_t *order);
+
 /* Runtime audit of the VERIFIED mode: with `every` = n > 0, each VERIFIED call re-polls every n-th detection in the
  * EXACT arithmetic on the same stream and counts the rows whose winning index differs (0 = off, the default; the
  * environment variable GPP_AUDIT=n sets it when a handle is created).  gpp_audit_counts returns the totals since

@@ -86,3 +86,28 @@ def test_product_package_never_imports_the_oracle():
                     src = fh.read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), (base, f)
                 assert 'libgpp_oracle' not in src, (base, f)
+
+
+def test_scan_order_is_a_permutation_that_groups_similar_planes(gpp):
+    """csrc/gpp_order.cu (host code, no device needed): the order the packed scans visit a database in is a
+    permutation; small databases keep the index order; rows of 64 consecutive positions hold similar planes, and the
+    first 8 rows are a sample of the whole parameter range."""
+    import numpy as np
+    from gpp_b200.layers.fit_road_planes import scan_order
+    small = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_1k.npy'))
+    assert np.array_equal(scan_order(small), np.arange(small.shape[0]))
+    for tag in ('10k', '22k'):
+        planes = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_%s.npy' % tag))
+        order = scan_order(planes)
+        n = planes.shape[0]
+        assert np.array_equal(np.sort(order), np.arange(n))
+        assert np.array_equal(order, scan_order(planes.astype(np.float32)))          # deterministic
+        p = planes * -np.sign(planes[:, 1:2])
+        p = p / np.linalg.norm(p[:, :3], axis=1, keepdims=True)
+        key = p[:, [0, 2, 3]] / p[:, [0, 2, 3]].std(0)
+        def spread(idx):                                     # typical extent of a row of 64 in the scaled parameters
+            rows = key[idx[:(len(idx) // 64) * 64]].reshape(-1, 64, 3)
+            return np.median(rows.max(1) - rows.min(1))
+        assert spread(order[512:]) < 0.5 * spread(np.arange(n)[512:])
+        seeds = key[order[:512]]
+        assert (seeds.max(0) - seeds.min(0) > 0.6 * (key.max(0) - key.min(0))).all()
