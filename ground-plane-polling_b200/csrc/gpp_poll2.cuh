@@ -251,9 +251,14 @@ __device__ __forceinline__ void eval_bottom(const DetConst &D, f2 n0, f2 n1, f2 
 
 // kMargin: 0 = none, 1 = out.m = geometric margin + mc, 2 = geometric margin only (the caller accounts for mc).
 // Sets out.r[0] (signed residual of the height) and leaves the SQUARED lengths of the slanted edges in ne / nf.
-template <int kMargin, bool kLazyZ>
-__device__ __forceinline__ void eval_top(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, const Bottom &g,
-                                         PairResult &out, f2 &ne, f2 &nf) {
+struct NoHook {
+    __device__ __forceinline__ void operator()(const DetConst &) const {}
+};
+// `before_r0`: called between the plane arithmetic and the first use of a residual target (the resident kernel fetches
+// the targets it has parked in shared memory there, gpp_poll3.cuh).
+template <int kMargin, bool kLazyZ, class D_, class Hook>
+__device__ __forceinline__ void eval_top(D_ &D, f2 n0, f2 n1, f2 n2, f2 d4, const Bottom &g,
+                                         PairResult &out, f2 &ne, f2 &nf, const Hook &before_r0) {
     const f2 u = fma2(n0, bc(D.ft[0]), fma2(n1, bc(D.ft[1]), n2));
     const f2 den = fma2(neg2(u), u, bc(D.T));
     const f2 iden = PackFast::rcp(den);
@@ -292,7 +297,13 @@ __device__ __forceinline__ void eval_top(const DetConst &D, f2 n0, f2 n1, f2 n2,
         ne = fma2(q, q, g.na);
         nf = fma2(q, q, g.nb);
     }
+    before_r0(D);
     out.r[0] = sub2(abs2(q), bc(D.td[0]));
+}
+template <int kMargin, bool kLazyZ>
+__device__ __forceinline__ void eval_top(const DetConst &D, f2 n0, f2 n1, f2 n2, f2 d4, const Bottom &g,
+                                         PairResult &out, f2 &ne, f2 &nf) {
+    eval_top<kMargin, kLazyZ>(D, n0, n1, n2, d4, g, out, ne, nf, NoHook());
 }
 
 template <bool kMergedRcp, int kMargin, bool kLazyZ = false>

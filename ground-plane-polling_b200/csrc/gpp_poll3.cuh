@@ -35,6 +35,9 @@
 #ifndef GPP_GENERAL_PREFETCH_EARLY
 #define GPP_GENERAL_PREFETCH_EARLY 1
 #endif
+#ifndef GPP_LAZY_Z6
+#define GPP_LAZY_Z6 true    /* z_dir_check of the all-six stage 2 is formed only by the rows that get that far (false: at once; measured 17.51 ms against 17.35 ms on C4) */
+#endif
 #ifndef GPP_TD3_READBACK
 #define GPP_TD3_READBACK 1
 #endif
@@ -98,21 +101,33 @@ __device__ __forceinline__ Detection<ExactF32> load_det_exact(const float *detx)
 // phase, the threshold updates) are parked in the warp's shared-memory slot and fetched where those paths begin, so that
 // the hot first stage keeps ten constants in registers instead of nineteen.
 constexpr int kColdOffset = 20;      // floats; the exact constants occupy [0, 18)
+// Two groups, each fetched where its first reader is (loaded earlier, the second group was parked in local memory across
+// eval_top by the compiler -- four local stores and three loads per stage-2 row): A = what eval_top reads, B = the
+// targets of the residuals that involve X_t and the rounding term of the margin.
 __device__ __forceinline__ void store_cold(float *detx, const DetConst &D) {
     float *c = detx + kColdOffset;
     c[0] = D.ft[0]; c[1] = D.ft[1]; c[2] = D.T; c[3] = D.G;
-    c[4] = D.msT; c[5] = D.mc; c[6] = D.td[0]; c[7] = D.td[4];
-    c[8] = D.td[5]; c[9] = D.msq;
+    c[4] = D.msT; c[5] = D.msq;
+    c[8] = D.td[0]; c[9] = D.td[4]; c[10] = D.td[5]; c[11] = D.mc;
+}
+__device__ __forceinline__ void load_cold_a(DetConst &D, const float *detx) {
+    const uint32_t a = smem_u32(detx + kColdOffset);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(D.ft[0]), "=f"(D.ft[1]), "=f"(D.T), "=f"(D.G) : "r"(a));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(D.msT), "=f"(D.msq) : "r"(a));
+}
+__device__ __forceinline__ void load_cold_b(DetConst &D, const float *detx) {
+    const uint32_t a = smem_u32(detx + kColdOffset);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(D.td[0]), "=f"(D.td[4]), "=f"(D.td[5]), "=f"(D.mc) : "r"(a));
 }
 __device__ __forceinline__ void load_cold(DetConst &D, const float *detx) {
-    const uint32_t a = smem_u32(detx + kColdOffset);
-    float x8, x9, pad1, pad2;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(D.ft[0]), "=f"(D.ft[1]), "=f"(D.T), "=f"(D.G) : "r"(a));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(D.msT), "=f"(D.mc), "=f"(D.td[0]), "=f"(D.td[4]) : "r"(a));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(x8), "=f"(x9), "=f"(pad1), "=f"(pad2) : "r"(a));
-    D.td[5] = x8;
-    D.msq = x9;
+    load_cold_a(D, detx);
+    load_cold_b(D, detx);
 }
+// eval_top hook: fetches group B between the plane arithmetic and the first residual that needs it
+struct ColdB {
+    const float *detx;
+    __device__ __forceinline__ void operator()(DetConst &D) const { load_cold_b(D, detx); }
+};
 
 // (max-votes, best residual) as one 64-bit key that grows when the pair improves: more votes first, then a smaller
 // residual (r >= +0, never NaN: the bit pattern orders like the value)
@@ -428,12 +443,12 @@ struct VerifiedScan {
 #else
         // stage 2: X_t, the height and the two slanted edges, the full margin
         GPP_STAT3(1, 1);
-        load_cold(D, detx);
+        load_cold_a(D, detx);
         ulonglong2 v0, v1;
         src.load_again(v0, v1);
         const f2 n0 = from_u64(v0.x), n1 = from_u64(v0.y), n2 = from_u64(v1.x), d4 = from_u64(v1.y);
         f2 ne, nf;
-        eval_top<2, true>(D, n0, n1, n2, d4, g, h, ne, nf);
+        eval_top<2, GPP_LAZY_Z6>(D, n0, n1, n2, d4, g, h, ne, nf, ColdB{detx});
         h.r[4] = sub2(PackFast::sqrt(abs2(ne)), bc(D.td[4]));
         h.r[5] = sub2(PackFast::sqrt(abs2(nf)), bc(D.td[5]));
         const f2 R = add2(add2(add2(S3, abs2(h.r[0])), abs2(h.r[4])), abs2(h.r[5]));
@@ -449,7 +464,7 @@ struct VerifiedScan {
         trig0 = trig0 && !(lo(rlo) > 0.7f);
         trig1 = trig1 && !(hi(rlo) > 0.7f);
         if (!__any_sync(0xffffffffu, trig0 || trig1)) return;
-        h.finish_zc();
+        if (GPP_LAZY_Z6) h.finish_zc();
         const f2 zhi = z_upper(h, D);               // upper bound of z_dir_check
         const f2 Rl2 = sub2(R, h.m);                // lower bound of the residual sum
         {
