@@ -9,11 +9,12 @@
 //   * a k-d tree over the normalised plane parameters (a, c, d) (b follows from the unit normal), each scaled by its
 //     standard deviation: the node's rows are halved along the coordinate with the largest variance until a leaf is one
 //     row of 64 planes;
-//   * a stratified sample of the leaves (8 rows = 512 planes, every (N/512)-th plane of the tree order) goes FIRST: it
+//   * a stratified sample of the leaves (16 rows = 1024 planes, every (N/1024)-th plane of the tree order) goes FIRST: it
 //     covers the parameter space evenly, so a scan has met a six-vote plane and a good residual bound after a few
 //     rows, whatever the detection, and visits the homogeneous rows with that bound in hand.
-// Measured on C4: rows past stage 1 31 % -> 18 %, general-phase rows dropped after the bottom face
-// 45 % -> 65 %.  Databases below 32 rows keep their order.
+// Measured on C4: rows of the all-six phase past stage 1 31 % -> 18 %, general-phase rows that leave
+// after the bottom face 45 % -> 63 %; 4, 8, 16 and 32 sample rows time within 1 % of each other.  Databases below 32
+// rows keep their order.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -29,7 +30,7 @@ namespace gpp {
 namespace {
 
 constexpr int kRow = 64;            // planes per row of the pair database
-constexpr int kSeedRows = 8;
+constexpr int kSeedRows = 16;
 constexpr int kMinRows = 32;
 
 struct Keys {
@@ -97,7 +98,9 @@ void scan_order(const float *rows, int n, std::vector<int32_t> &order) {
     std::iota(idx.begin(), idx.end(), 0);
     split(idx.data(), n_rows, n, K);
     // the stratified sample first, the rest in tree order
-    const int n_seed = kSeedRows * kRow;
+    int seed_rows = kSeedRows;
+    if (const char *env = getenv("GPP_SEED_ROWS")) seed_rows = std::max(1, std::min(atoi(env), n_rows / 2));   // measurements only
+    const int n_seed = seed_rows * kRow;
     std::vector<char> seed((size_t)n, 0);
     for (int i = 0; i < n_seed; ++i) seed[(size_t)(((double)i + 0.5) * n / n_seed)] = 1;
     size_t at = 0;

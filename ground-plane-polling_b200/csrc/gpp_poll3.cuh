@@ -27,25 +27,12 @@
 #include "gpp_poll2.cuh"
 #include "gpp_pose.cuh"
 
-#ifdef GPP_NO_XLATE
-#define GPP_XLATE(p) (p)
-#else
-#define GPP_XLATE(p) __ldg(scan_index + (p))
-#endif
-#ifndef GPP_GENERAL_PREFETCH_EARLY
-#define GPP_GENERAL_PREFETCH_EARLY 1
-#endif
 #ifndef GPP_LAZY_Z6
 #define GPP_LAZY_Z6 true    /* z_dir_check of the all-six stage 2 is formed only by the rows that get that far (false: at once; measured 17.51 ms against 17.35 ms on C4) */
 #endif
-#ifndef GPP_TD3_READBACK
-#define GPP_TD3_READBACK 1
-#endif
-#ifndef GPP_TWO_LOOPS
-#define GPP_TWO_LOOPS 1
-#endif
 #ifndef GPP_GEN_EXIT
-#define GPP_GEN_EXIT 0
+#define GPP_GEN_EXIT 1      /* general phase: rows leave after the bottom face when no plane can matter (0: measured equal at the
+                             benchmark's 1.5 px key-point noise, 4 % / 6 % slower at 4 px / 10 px) */
 #endif
 #ifndef GPP_STAGE2
 #define GPP_STAGE2 1      /* 0: experiment -- stage-1 survivors of the all-six phase go straight to the exact queue */
@@ -379,9 +366,9 @@ struct VerifiedScan {
         if (b0 | b1) {
             GPP_STAT3(7, 1);
             const unsigned below = (1u << lane) - 1u;
-            if (q0) queue[qn + __popc(b0 & below)] = GPP_XLATE(pos);       // the queue holds plane indices
+            if (q0) queue[qn + __popc(b0 & below)] = __ldg(scan_index + pos);       // the queue holds plane indices
             qn += __popc(b0);
-            if (q1) queue[qn + __popc(b1 & below)] = GPP_XLATE(pos + 1);
+            if (q1) queue[qn + __popc(b1 & below)] = __ldg(scan_index + pos + 1);
             qn += __popc(b1);
             __syncwarp();
             const bool flush_all = __any_sync(0xffffffffu, urgent);
@@ -402,15 +389,8 @@ struct VerifiedScan {
         bool trig0, trig1, urgent = false;
         Bottom g;
         eval_dots(D, from_u64(c0.x), from_u64(c0.y), from_u64(c1.x), from_u64(c1.y), g);
-#if GPP_GENERAL_PREFETCH_EARLY
         if (src.more()) src.load_next<kStep>(c0, c1);
         if (!general_row(D, src, g, h, trig0, trig1, urgent, detx)) return;
-#else
-        // the next row is fetched once the row's registers are free again
-        const bool keep = general_row(D, src, g, h, trig0, trig1, urgent, detx);
-        if (src.more()) src.load_next<kStep>(c0, c1);
-        if (!keep) return;
-#endif
         enqueue(trig0, trig1, urgent, src, N, lane, queue, detx, planes, scan_index, D);
     }
 
@@ -484,14 +464,6 @@ struct VerifiedScan {
         trig1 = !(hi(Rl2) > wbest) && !(hi(rlo) > 0.7f) && !(hi(zhi) < 0.0f);
 #endif
         enqueue(trig0, trig1, false, src, N, lane, queue, detx, planes, scan_index, D);
-    }
-
-    template <bool kStep>
-    __device__ __forceinline__ void row(const DetConst &Dh, const RowSource &src, ulonglong2 &c0, ulonglong2 &c1,
-                                        const int N, const int lane, int *queue, const float *detx,
-                                        const float4 *__restrict__ planes, const int32_t *__restrict__ scan_index) {
-        if (Mcur == 6) row_six<kStep>(Dh, src, c0, c1, N, lane, queue, detx, planes, scan_index);
-        else row_general<kStep>(Dh, src, c0, c1, N, lane, queue, detx, planes, scan_index);
     }
 
     // end of the segment: the last partial batch; afterwards `st` holds the exact result of the scanned planes
@@ -803,12 +775,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 store_cold(detx, D);
             }
             __syncwarp();
-#if GPP_TD3_READBACK
             // td[3] comes out of an IEEE square root (a subroutine call the compiler cannot see through): read back from
             // the warp's slot it is a load from a warp-uniform address, and joins the other hot constants in a uniform
             // register instead of being reloaded from local memory on every row
             D.td[3] = detx[15];
-#endif
         }
 
         int Mw, idx;
@@ -850,7 +820,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                         sc.adopt(__shfl_sync(0xffffffffu, key, 0), detx);
                     }
                 };
-#if GPP_TWO_LOOPS
                 for (; src.rows_left > 0 && sc.Mcur < 6; src.advance<kSeg>()) {
                     sc.row_general<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
                     exchange();
@@ -859,12 +828,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                     sc.row_six<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
                     exchange();
                 }
-#else
-                for (; src.rows_left > 0; src.advance<kSeg>()) {
-                    sc.row<kSeg>(D, src, c0, c1, N, lane, queue, detx, args.planes, args.scan_index);
-                    exchange();
-                }
-#endif
                 sc.finish(detx, args.planes, queue, lane);
                 sc.result(Mw, rb, idx);
             } else {

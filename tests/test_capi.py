@@ -91,7 +91,7 @@ def test_product_package_never_imports_the_oracle():
 def test_scan_order_is_a_permutation_that_groups_similar_planes(gpp):
     """csrc/gpp_order.cu (host code, no device needed): the order the packed scans visit a database in is a
     permutation; small databases keep the index order; rows of 64 consecutive positions hold similar planes, and the
-    first 8 rows are a sample of the whole parameter range."""
+    first 16 rows are a sample of the whole parameter range."""
     import numpy as np
     from gpp_b200.layers.fit_road_planes import scan_order
     small = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_1k.npy'))
@@ -108,6 +108,7 @@ def test_scan_order_is_a_permutation_that_groups_similar_planes(gpp):
         def spread(idx):                                     # typical extent of a row of 64 in the scaled parameters
             rows = key[idx[:(len(idx) // 64) * 64]].reshape(-1, 64, 3)
             return np.median(rows.max(1) - rows.min(1))
-        assert spread(order[512:]) < 0.5 * spread(np.arange(n)[512:])
-        seeds = key[order[:512]]
-        assert (seeds.max(0) - seeds.min(0) > 0.6 * (key.max(0) - key.min(0))).all()
+        assert spread(order[1024:]) < 0.5 * spread(np.arange(n)[1024:])
+        seeds = key[order[:1024]]
+        pr = lambda a: np.percentile(a, 99, axis=0) - np.percentile(a, 1, axis=0)    # noqa: E731  (the 10k database has outliers)
+        assert (pr(seeds) > 0.6 * pr(key)).all()
