@@ -149,6 +149,7 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     int n_seg = 1;
     if (h->force_seg > 0) n_seg = h->force_seg;
     else if (n_rows < 3 * slots) n_seg = (int)((3 * slots + n_rows - 1) / n_rows);
+    if (h->force_seg <= 0 && n_seg > 24) n_seg = 24;      // a single image: 0.038 ms with 24 segments, 0.045 ms with 32
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;
     if (n_rows > h->seg_det_cap || n_rows * n_seg > h->seg_items_cap) n_seg = 1;

@@ -164,6 +164,9 @@ struct RowSource {
     template <bool kStep>
     __device__ __forceinline__ void advance() {
         saddr += kStep ? step_bytes : 1024u;
+        // with a run-time step the compiler otherwise keeps four running addresses (this row, the next one, both again as
+        // global offsets) and spills one of them: one running address, the others derived where they are used
+        if (kStep) asm volatile("" : "+r"(saddr));
         --rows_left;
         res_left -= kStep ? int(step_bytes >> 10) : 1;
     }
@@ -231,17 +234,12 @@ struct VerifiedScan {
 
     // adopt a bound found by another segment of the same detection (exact values, published through seg_best)
     __device__ __forceinline__ void adopt(unsigned long long key, const float *detx) {
-        DetConst D;
-        load_cold(D, detx);
         const int M = int(unsigned(key >> 32)) - 1;
         const float r = __uint_as_float(0xffffffffu - unsigned(key & 0xffffffffu));
-        if (M > Mcur) {
+        if (M > Mcur || (M == Mcur && r < wbest)) {
             Mcur = M;
             wbest = r;
-            wthr = (wbest + D.mc) * 1.0000038f;
-        } else if (M == Mcur && r < wbest) {
-            wbest = r;
-            wthr = (wbest + D.mc) * 1.0000038f;
+            wthr = (wbest + detx[kColdOffset + 11]) * 1.0000038f;       // mc
         }
     }
 
@@ -348,9 +346,20 @@ struct VerifiedScan {
                 0xffffffffu, __float_as_uint(fminf(c0 ? lo(Rhi) : FLT_MAX, c1 ? hi(Rhi) : FLT_MAX))));
             wbest = fminf(wbest, e);
         }
+        urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
+        if (__any_sync(0xffffffffu, urgent)) {
+            // Votes that some plane of this row CERTAINLY has: if that is more than Mcur, max-votes ends up at L or above
+            // whatever the others do, and only the planes that may reach L can still matter.  (The first row of every
+            // scan starts from Mcur = -1: without this all its 64 planes would be verified.)
+            const int L = __reduce_max_sync(0xffffffffu, max(strict_votes(h, false), strict_votes(h, true)));
+            if (L > Mcur) {
+                trig0 = V0 >= L;
+                trig1 = V1 >= L;
+                return true;
+            }
+        }
         trig0 = (V0 > Mcur) || (k0 && !(lo(Rlo) > wbest));
         trig1 = (V1 > Mcur) || (k1 && !(hi(Rlo) > wbest));
-        urgent = (V0 > Mcur) || (V1 > Mcur);            // may raise max-votes: verify right away
         return true;
     }
 
@@ -637,13 +646,15 @@ __device__ __forceinline__ void update_unordered(LaneState<T> &st, int V, T R, b
     st.M = max(st.M, V);
 }
 
-template <class P>
+template <class P, class Q>
 __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typename P::T4 *__restrict__ planes,
                                             const int32_t *__restrict__ index, const int first_row, const int row_step,
                                             const int n_planes, const int lane, const bool same_rays,
                                             LaneState<typename P::T> &st) {
     typedef typename P::T T;
     typedef typename P::T4 T4;
+    // Q: P, or the same arithmetic with independent divisions / square roots paired (the EXACT mode's own scan)
+    const Detection<Q> &dq = reinterpret_cast<const Detection<Q> &>(det);      // same layout
     const T highest = P::highest();
     const T thr = P::thresh();
     st.reset(highest);
@@ -654,7 +665,7 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
             const T4 pl = planes[p];
             T X[4][3];
             int V; T R; bool z;
-            hypothesis_same_rays<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
+            hypothesis_same_rays<Q>(dq, pl.x, pl.y, pl.z, pl.w, X, V, R, z);
             update_unordered(st, V, R, z, index ? __ldg(index + p) : p, highest);
         }
         return;
@@ -671,19 +682,19 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
         int V; T R; bool zneg;
         if (Mw >= 5) {
             T rb[3];
-            rb[2] = bottom_lr<P>(det, pl.x, pl.y, pl.z, pl.w, X);
+            rb[2] = bottom_lr<Q>(dq, pl.x, pl.y, pl.z, pl.w, X);
             if (!__any_sync(0xffffffffu, valid && (!(rb[2] > wbest) || (Mw == 5 && !(rb[2] > thr))))) continue;
-            bottom_m<P>(det, pl.x, pl.y, pl.z, pl.w, X, rb);
+            bottom_m<Q>(dq, pl.x, pl.y, pl.z, pl.w, X, rb);
             const T S3 = P::add(P::add(rb[0], rb[1]), rb[2]);
             const bool all3 = !(rb[0] > thr) && !(rb[1] > thr) && !(rb[2] > thr);
             if (!__any_sync(0xffffffffu, valid && (!(S3 > wbest) || (Mw == 5 && all3)))) continue;
-            zneg = bottom_zneg<P>(X);
-            hypothesis_top<P>(det, pl.x, pl.y, pl.z, X, rb, V, R);
+            zneg = bottom_zneg<Q>(X);
+            hypothesis_top<Q>(dq, pl.x, pl.y, pl.z, X, rb, V, R);
             if (valid) update_unordered(st, V, R, zneg, index ? __ldg(index + p) : p, highest);
             Mw = __reduce_max_sync(0xffffffffu, st.M);
             wbest = warp_min_value(st.M == Mw ? st.bestR : highest);
         } else {
-            hypothesis<P>(det, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
+            hypothesis<Q>(dq, pl.x, pl.y, pl.z, pl.w, X, V, R, zneg);
             if (valid) update_unordered(st, V, R, zneg, index ? __ldg(index + p) : p, highest);
             if ((it & 3) == 3) {
                 Mw = __reduce_max_sync(0xffffffffu, st.M);
@@ -790,10 +801,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             if constexpr (kPacked) det = load_det_exact(detx); else det = detE;
             LaneState<T> st;
             if constexpr (kMode == kModeF64)
-                scalar_scan<P>(det, planesT, nullptr, seg, n_seg, N, lane, same_rays, st);
+                scalar_scan<P, P>(det, planesT, nullptr, seg, n_seg, N, lane, same_rays, st);
+            else if constexpr (kMode == kModeExact)
+                scalar_scan<P, typename PairedOf<P>::type>(det, reinterpret_cast<const T4 *>(args.planes_scan),
+                                                           args.scan_index, seg, n_seg, N, lane, same_rays, st);
             else
-                scalar_scan<P>(det, reinterpret_cast<const T4 *>(args.planes_scan), args.scan_index, seg, n_seg, N, lane,
-                               same_rays, st);
+                scalar_scan<P, P>(det, reinterpret_cast<const T4 *>(args.planes_scan), args.scan_index, seg, n_seg, N, lane,
+                                  same_rays, st);
             Mw = __reduce_max_sync(0xffffffffu, st.M);
             rbest = (st.M == Mw) ? st.bestR : P::highest();
             idx = st.bestIdx;
@@ -813,6 +827,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 // segments of one detection share their bounds: every fourth row a warp publishes its own (one atomicMax
                 // on the detection's 64-bit key) and adopts the best published so far (one uniform branch per row; the
                 // round-2 profile of C3 showed the per-row form of this exchange at 40 instructions a row)
+                // (exchanging on every row of the general phase, whose rows cost three of the others, was measured: C3 0.262 ms
+                // against 0.245 ms)
                 auto exchange = [&]() {
                     if (kSeg && (src.rows_left & 3) == 1) {
                         unsigned long long key = seg_key(sc.Mcur, sc.wbest);
