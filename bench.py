@@ -52,7 +52,7 @@ if ROOT not in sys.path:
 W_ALG = 148.0                      # algorithmic FLOP per hypothesis, SURVEY.md section 8.4
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 KERNEL_OF_MODE = {'verified': 'gpp::poll3_kernel<32, verified>',
-                  'fast': 'gpp::poll3_kernel<32, fast>', 'exact': 'gpp::poll_kernel<ExactF32>'}
+                  'fast': 'gpp::poll3_kernel<32, fast>', 'exact': 'gpp::poll3_kernel<32, exact>'}
 METRIC = 'ground-plane hypotheses/sec (dets x planes)'
 UNIT = 'hypotheses/s'
 

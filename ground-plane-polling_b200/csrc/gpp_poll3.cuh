@@ -155,6 +155,9 @@ struct RowSource {
         }
     }
     __device__ __forceinline__ bool more() const { return rows_left > 1; }
+    // (A branch-free form -- the current row again on the last row, so that the compiler cannot sink the loads behind the
+    // `more()` test to the end of the row -- was measured: the loads do move up and the wait at the top of the next row
+    // goes, but C4 takes 17.29 ms against 17.11 ms and the FAST mode 16.1 ms against 15.3 ms.)
     template <bool kStep>
     __device__ __forceinline__ void load_next(ulonglong2 &a, ulonglong2 &b) const {
         if (kStep) load(res_left > int(step_bytes >> 10), saddr + step_bytes, a, b);
