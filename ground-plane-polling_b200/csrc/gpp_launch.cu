@@ -124,8 +124,9 @@ void release_poll3(gpp_handle *h) {
 // Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below three detections per resident warp every
 // detection is cut into plane segments so that the work items still fill the machine about three times over (the
 // last wave is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs
-// three times the average -- is long enough to be the tail; at most 32).  Tried and dropped (r02): whole rows first
-// and segments only for the last partial wave (64 x 100 x 10k: 0.32 ms against 0.26 ms).  Residency:
+// three times the average -- is long enough to be the tail; at most 24 unless forced).  Tried and dropped (r02): whole
+// rows first and segments only for the last partial wave (64 x 100 x 10k: 0.32 ms against 0.26 ms); two segments for a
+// 512-image shard of an 8-GPU call (2.67 ms against 2.47 ms).  Residency:
 // staging up to 212 KB per SM pays as soon as every warp polls a few items; a call with fewer items than that streams
 // every row from L2 and starts at once.
 static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride, cudaStream_t s) {
