@@ -380,7 +380,8 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
 
 def fit_road_planes_torch(boxes, dimensions, orientations, P_inv, planes, mode=None, return_index=False,
                           return_pose=False, return_kitti=False):
-    """Same operator on CUDA tensors (zero-copy, torch's current stream, no host sync).  ``planes`` is one
+    """Same operator on CUDA tensors (zero-copy, torch's current stream, no host sync once the database is resident:
+    a NEW device-resident database of 2048 planes or more is read back once to derive its scan order).  ``planes`` is one
     (N, 4) / (1, N, 4) database shared by the batch (torch tensor on any device, or numpy).  ``return_pose`` appends
     locations, angles and corrected dimensions, (B, D, 3) each, ``return_kitti`` the (B, D, 4) KITTI records -- computed in
     the polling kernel's epilogue."""

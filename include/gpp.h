@@ -76,7 +76,9 @@ int gpp_set_planes(gpp_handle *h, const float *planes, int n_planes);
  * (run_network.py:105) costs one memcmp. */
 int gpp_set_planes_raw(gpp_handle *h, const void *planes, int n_planes, int dtype, int order);
 /* Same, from a device pointer (stream-ordered on `stream`, no shortcut; fits of this handle still in flight on other
- * streams are waited for, and later fits on other streams wait for the update). */
+ * streams are waited for, and later fits on other streams wait for the update).  A database of 2048 planes or more is
+ * read back to the host once per update to derive the order it is scanned in (csrc/gpp_order.cu): that update blocks the
+ * caller until `stream` has caught up (inside a stream capture the index order is kept instead). */
 int gpp_set_planes_device(gpp_handle *h, const float *d_planes, int n_planes, void *stream);
 int gpp_num_planes(const gpp_handle *h);
 /* Copy the normalised database (N x 4 floats) back to host -- the table `keyplanes` rows are taken from. */
