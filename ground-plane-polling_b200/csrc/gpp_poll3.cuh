@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 // on the detection's 64-bit key) and adopts the best published so far (one uniform branch per row; the
                 // round-2 profile of C3 showed the per-row form of this exchange at 40 instructions a row)
                 // (exchanging on every row of the general phase, whose rows cost three of the others, was measured: C3 0.262 ms
-                // against 0.245 ms)
+                // against 0.245 ms; so was a form that never waits -- the key read at the top of every row, adopted at its end,
+                // published by a reduction without a result: 0.248 ms, no different)
                 auto exchange = [&]() {
                     if (kSeg && (src.rows_left & 3) == 1) {
                         unsigned long long key = seg_key(sc.Mcur, sc.wbest);
