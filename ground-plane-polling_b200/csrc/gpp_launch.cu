@@ -1,6 +1,6 @@
 // Launch configuration of the polling kernel (gpp_poll3.cuh), the once-per-database pair interleave, the runtime audit
 // and the per-hypothesis score kernels of the test hooks.
-#ifdef GPP_STATS
+#if defined(GPP_STATS) || defined(GPP_TIMELINE)
 #include <cstdio>
 #endif
 #include "../../include/gpp_debug.h"
@@ -168,6 +168,31 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     if (grid > n_items) grid = n_items;
     const size_t smem = smem3_bytes(warps, res);
     poll3_variant(mode, b.n_seg > 1, b.pose_locations != nullptr)<<<(unsigned)grid, warps * 32, smem, s>>>(b);
+#ifdef GPP_TIMELINE
+    {
+        static unsigned long long host_tl[8192][6];
+        unsigned int n = 0, zero = 0;
+        cudaEvent_t e0, e1;
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(&n, g_timeline_n, sizeof(n));
+        cudaMemcpyFromSymbol(host_tl, g_timeline, sizeof(host_tl));
+        cudaMemcpyToSymbol(g_timeline_n, &zero, sizeof(zero));
+        if (n > 8192) n = 8192;
+        unsigned long long t_min = ~0ull, t_max = 0;
+        for (unsigned i = 0; i < n; ++i) { if (host_tl[i][1] < t_min) t_min = host_tl[i][1]; if (host_tl[i][3] > t_max) t_max = host_tl[i][3]; }
+        fprintf(stderr, "[gpp timeline] %u records, n_seg %d, span %.2f us\n", n, b.n_seg, (t_max - t_min) * 1e-3);
+        for (unsigned i = 0; i < n; ++i) {
+            if (host_tl[i][5] >> 63)
+                fprintf(stderr, "[tl] item %llu kind 1 same_rays 0 start %.2f a %.2f b %.2f c %.2f d %.2f\n", host_tl[i][0],
+                        (host_tl[i][1] - t_min) * 1e-3, (host_tl[i][2] - t_min) * 1e-3, (host_tl[i][4] - t_min) * 1e-3,
+                        ((host_tl[i][5] & ~(1ull << 63)) - t_min) * 1e-3, (host_tl[i][3] - t_min) * 1e-3);
+            else
+                fprintf(stderr, "[tl] item %llu kind %llu same_rays %llu start %.2f a %.2f b %.2f\n", host_tl[i][0], host_tl[i][5], host_tl[i][4],
+                        (host_tl[i][1] - t_min) * 1e-3, (host_tl[i][2] - t_min) * 1e-3, (host_tl[i][3] - t_min) * 1e-3);
+        }
+        (void)e0; (void)e1;
+    }
+#endif
 #ifdef GPP_STATS
     if (mode == GPP_MODE_VERIFIED) {
         unsigned long long st[10], zero[10] = {0};

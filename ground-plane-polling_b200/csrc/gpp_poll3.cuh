@@ -184,6 +184,18 @@ struct RowSource {
 // [2] rows in the general phase, [3] exact verifications, [4] flushes, [5] work items, [6] items polled in the
 // identical-rays form, [7] rows past the whole filter (something queued), [8] general-phase rows (max-votes >= 4) past
 // the bottom-face test, [9] general-phase rows at max-votes >= 4
+#ifdef GPP_TIMELINE   /* development only: per-item time stamps (globaltimer, ns), printed by launch_poll3 */
+__device__ unsigned long long g_timeline[8192][6];
+__device__ unsigned int g_timeline_n;
+__device__ __forceinline__ unsigned long long gpp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GPP_TL(var) const unsigned long long var = gpp_now()
+#else
+#define GPP_TL(var) ((void)0)
+#endif
 #ifdef GPP_STATS
 __device__ unsigned long long g_stats3[10];
 #define GPP_STAT3(i, n) (stat[i] += (n))
@@ -662,7 +674,10 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
     const T thr = P::thresh();
     st.reset(highest);
     if (same_rays) {
-        // FilterDetections' padding rows: the cheap form that identical rays allow (bit-identical, gpp_math.cuh)
+        // FilterDetections' padding rows: the cheap form that identical rays allow (bit-identical, gpp_math.cuh).  (A
+        // padded image has ONE such row, and its scan is a chain of dependent arithmetic on a nearly empty machine: 19 us of
+        // a 50 us single-image call.  Fetching the plane a step ahead, unrolling by four, or moving the loop out of line
+        // each cost the packed scan loops of the same kernel their spill-free register allocation.)
 #pragma unroll 2
         for (int p = (first_row << 5) + lane; p < n_planes; p += row_step << 5) {
             const T4 pl = planes[p];
@@ -704,6 +719,18 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
                 wbest = warp_min_value(st.M == Mw ? st.bestR : highest);
             }
         }
+    }
+}
+
+// `run` consecutive rows of kWords words each, all equal to the words that lanes first_lane .. first_lane + kWords - 1 hold
+// in `value`: written as one coalesced stream
+template <int kWords, class V>
+__device__ __forceinline__ void emit_rows(V *dst, long long run, V value, int first_lane, int lane) {
+    const long long total = kWords * run;
+    for (long long base = 0; base < total; base += 32) {
+        const long long i = base + lane;
+        const V v = __shfl_sync(0xffffffffu, value, first_lane + int(i % kWords));
+        if (i < total) dst[i] = v;
     }
 }
 
@@ -752,14 +779,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
     const int stride = args.det_stride;
     const unsigned long long n_rows = (unsigned long long)((args.n_det + stride - 1) / stride);
     const unsigned long long n_items = n_rows * (unsigned)n_seg;
-    unsigned long long next_claim = 0;
-    if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);
-    next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+    // The first item of every warp is fixed (warp w of CTA b: item w * gridDim + b, so that the items of a small call
+    // spread over all SMs): a launch does not begin with 4736 atomics on one address.  The counter hands out the rest.
+    unsigned long long next_claim = (unsigned long long)(warp * gridDim.x + blockIdx.x);
+    next_claim = __shfl_sync(0xffffffffu, next_claim, 0);       // (keeps the compiler from specialising the first round)
 
     for (;;) {
         const unsigned long long item = next_claim;
         if (item >= n_items) break;                                  // warp-uniform: this warp retires
-        if (lane == 0) next_claim = atomicAdd(args.claim, 1ull);     // claimed one item ahead
+        if (lane == 0) next_claim = atomicAdd(args.claim, 1ull) + gridDim.x * kWarps;     // claimed one item ahead
         next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
         const long long slot = kSeg ? (long long)(item / (unsigned)n_seg) : (long long)item;   // index into the scratch
         const int seg = kSeg ? int(item - (unsigned long long)slot * (unsigned)n_seg) : 0;
@@ -767,6 +795,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
         // a row that repeats the previous row of its image is written by the warp that polls that row
         if (stride == 1 && (m % args.dets_per_image) != 0 && same_detection(args, m, m - 1, lane)) continue;
 
+        GPP_TL(tl0);
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
         Detection<P> detE;
         load_detection<P, P>(detE, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
@@ -795,6 +824,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             D.td[3] = detx[15];
         }
 
+        GPP_TL(tl1);
         int Mw, idx;
         T rbest;
         if (!kPacked || (kVerified && same_rays)) {
@@ -859,6 +889,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             rbest = rb;
         }
         rbest = warp_min_first(rbest, idx);
+        GPP_TL(tl2);
+#ifdef GPP_TIMELINE
+        if (lane == 0 && kSeg) {
+            const unsigned k = atomicAdd(&g_timeline_n, 1u);
+            if (k < 8192) { g_timeline[k][0] = item; g_timeline[k][1] = tl0; g_timeline[k][2] = tl1; g_timeline[k][3] = tl2; g_timeline[k][4] = same_rays; g_timeline[k][5] = 0; }
+        }
+#endif
 
         if (kSeg) {
             // ---- hand the partial result in; the warp that completes the detection merges and continues
@@ -888,6 +925,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             }
         }
 
+        GPP_TL(tl3);
         // ---- epilogue: lazy first-masked search, exact recompute of the winner (fit_road_planes.py:116-137)
         Detection<P> det;
         if constexpr (kPacked) det = load_det_exact(detx); else det = detE;
@@ -976,6 +1014,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
                 for (int i = 0; i < 4; ++i) pword = (lane == 9 + i) ? rec[i] : pword;
             }
         }
+        GPP_TL(tl4);
         // this row and the identical rows that follow it in the image (their claims were skipped).  The length of
         // the run is found 32 rows at a time -- lane i compares row m + 1 + i with its predecessor -- so that a
         // padded image costs a few load latencies, not one per padding row.
@@ -999,20 +1038,43 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             run_end = base + (lead < 0 ? 32 : lead);
             if (lead >= 0) break;
         }
+        GPP_TL(tl5);
         T *kp_out = static_cast<T *>(args.keypoints), *kpl_out = static_cast<T *>(args.keyplanes);
         T *res_out = static_cast<T *>(args.residuals);
-        for (long long n = m; n < run_end; ++n) {
-            if (lane < 12) kp_out[12 * n + lane] = word;
-            else if (lane < 16) kpl_out[4 * n + (lane - 12)] = word;
-            else if (lane == 16) res_out[n] = word;
-            else if (lane == 17 && args.best) args.best[n] = idx;
+        if (run_end == m + 1) {
+            if (lane < 12) kp_out[12 * m + lane] = word;
+            else if (lane < 16) kpl_out[4 * m + (lane - 12)] = word;
+            else if (lane == 16) res_out[m] = word;
+            else if (lane == 17 && args.best) args.best[m] = idx;
             if constexpr (kPose) {
-                if (lane < 3) args.pose_locations[3 * n + lane] = pword;
-                else if (lane < 6) args.pose_angles[3 * n + (lane - 3)] = pword;
-                else if (lane < 9) args.pose_dimensions[3 * n + (lane - 6)] = pword;
-                else if (lane < 13 && args.pose_kitti) args.pose_kitti[4 * n + (lane - 9)] = pword;
+                if (lane < 3) args.pose_locations[3 * m + lane] = pword;
+                else if (lane < 6) args.pose_angles[3 * m + (lane - 3)] = pword;
+                else if (lane < 9) args.pose_dimensions[3 * m + (lane - 6)] = pword;
+                else if (lane < 13 && args.pose_kitti) args.pose_kitti[4 * m + (lane - 9)] = pword;
+            }
+        } else {
+            // a run of identical rows (a padded image: up to 99 of them): every output array as one coalesced stream, the
+            // lanes spread over the rows (row by row -- four partial stores per row -- the 85 padding rows of an image
+            // took 13 us, a third of a single-image call)
+            const long long run = run_end - m;
+            emit_rows<12>(kp_out + 12 * m, run, word, 0, lane);
+            emit_rows<4>(kpl_out + 4 * m, run, word, 12, lane);
+            emit_rows<1>(res_out + m, run, word, 16, lane);
+            if (args.best)
+                for (long long i = lane; i < run; i += 32) args.best[m + i] = idx;
+            if constexpr (kPose) {
+                emit_rows<3>(args.pose_locations + 3 * m, run, pword, 0, lane);
+                emit_rows<3>(args.pose_angles + 3 * m, run, pword, 3, lane);
+                emit_rows<3>(args.pose_dimensions + 3 * m, run, pword, 6, lane);
+                if (args.pose_kitti) emit_rows<4>(args.pose_kitti + 4 * m, run, pword, 9, lane);
             }
         }
+#ifdef GPP_TIMELINE
+        if (lane == 0) {
+            const unsigned k = atomicAdd(&g_timeline_n, 1u);
+            if (k < 8192) { g_timeline[k][0] = item; g_timeline[k][1] = tl2; g_timeline[k][2] = tl3; g_timeline[k][3] = gpp_now(); g_timeline[k][4] = tl4; g_timeline[k][5] = tl5 | (1ull << 63); }
+        }
+#endif
     }
 
     // ---- the last CTA to leave resets the counters for the next launch
