@@ -239,6 +239,28 @@ def test_torch_database_is_never_stale(gpp, poller):
         gpp.fit_road_planes_torch(*t, tiled.contiguous(), mode='exact')
 
 
+def test_large_device_fed_database_gets_the_scan_order(gpp, poller):
+    """A database of 32 rows or more that arrives as a CUDA tensor is read back once to derive the order it is scanned
+    in (csrc/gpp_order.cu); the results are those of the host-fed database in every mode, on any stream."""
+    import torch
+    dev = torch.device('cuda', 0)
+    planes = load_planes('10k')
+    boxes, dims, orient, P_inv = synthetic.synth_detections(3, 100, planes, seed=91, n_valid=70)
+    t = [torch.from_numpy(a).to(dev) for a in (boxes, dims, orient, P_inv.astype(np.float32))]
+    want = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, planes, return_index=True)
+    host_fed = {m: gpp.fit_road_planes(boxes, dims, orient, P_inv, planes, mode=m, return_index=True) for m in ('fast', 'f64')}
+    poller.set_planes(load_planes('100'))                          # something else resident in between
+    tpl = torch.from_numpy(planes.astype(np.float32)).to(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        got = {m: gpp.fit_road_planes_torch(*t, tpl, mode=m, return_index=True) for m in ('verified', 'exact', 'fast')}
+    side.synchronize()
+    for m in ('verified', 'exact'):
+        _assert_identical([o.cpu().numpy() for o in got[m]], want)
+    _assert_identical([o.cpu().numpy() for o in got['fast']], host_fed['fast'])
+
+
 def test_tiled_numpy_databases_are_grouped_exactly(gpp):
     """(B, N, 4) databases as preprocessing/kitti.py:220 tiles them: one upload for a true tile, per-image groups when
     one image's copy differs in a single value"""
