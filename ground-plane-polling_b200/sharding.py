@@ -141,14 +141,22 @@ def _fit_multi_native(boxes, dimensions, orientations, P_inv, planes, devices, m
         raise ValueError('inconsistent shapes: boxes %r dimensions %r orientations %r P_inv %r' % (
             boxes.shape, dimensions.shape, orientations.shape, P_inv.shape))
     pollers = [get_poller(d) for d in devices]
-    for p in pollers:
-        p.set_planes(planes)                     # one memcmp per device when the database is the one already resident
+    # the database goes along as the caller holds it (float64 / Fortran order from loadmat included): every device compares
+    # it with what it holds -- and uploads it if it differs -- from its shard's thread
+    pl = np.asarray(planes)
+    if pl.ndim != 2 or pl.shape[1] != 4 or pl.shape[0] < 1:
+        raise ValueError('planes must have shape (N, 4) with N >= 1, got %r' % (pl.shape,))
+    if pl.dtype not in (np.float32, np.float64) or not (pl.flags['C_CONTIGUOUS'] or pl.flags['F_CONTIGUOUS']):
+        pl = _f32(pl)
     b, d, p_inv = _f32(boxes), _f32(dimensions), _f32(P_inv)
     o = np.ascontiguousarray(orientations, dtype=np.int32)
     handles = (ctypes.c_void_p * len(pollers))(*[p._h for p in pollers])
     lib = _lib.load()
-    rc = lib.gpp_fit_host_multi(handles, len(pollers), _lib.ptr(b), _lib.ptr(d), _lib.ptr(o), _lib.ptr(p_inv), B, D,
-                                _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
-                                _lib.ptr(out[3]) if return_index else None, _lib.MODES[mode])
-    _lib.check(rc, 'gpp_fit_host_multi')
+    rc = lib.gpp_fit_host_multi_planes(handles, len(pollers), pl.ctypes.data, pl.shape[0], 1 if pl.dtype == np.float64 else 0,
+                                       0 if pl.flags['C_CONTIGUOUS'] else 1, _lib.ptr(b), _lib.ptr(d), _lib.ptr(o),
+                                       _lib.ptr(p_inv), B, D, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+                                       _lib.ptr(out[3]) if return_index else None, _lib.MODES[mode])
+    for p in pollers:
+        p._dev_planes = None
+    _lib.check(rc, 'gpp_fit_host_multi_planes')
     return out

@@ -107,6 +107,13 @@ int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, con
 int gpp_fit_host_multi(gpp_handle **handles, int n_handles, const float *boxes, const float *dimensions,
                        const int32_t *orientations, const float *P_inv, int B, int D, float *keypoints,
                        float *keyplanes, float *residuals, int64_t *best_index, int mode);
+/* Same, with the plane database of gpp_set_planes_raw in the same call: every handle compares it with what it holds (and
+ * uploads it if it differs) from its shard's thread, so the callers' "feed the database with every batch"
+ * (run_network.py:105) costs one concurrent memcmp per device instead of one after the other. */
+int gpp_fit_host_multi_planes(gpp_handle **handles, int n_handles, const void *planes, int n_planes, int dtype, int order,
+                              const float *boxes, const float *dimensions, const int32_t *orientations,
+                              const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
+                              int64_t *best_index, int mode);
 
 /* Device entry (the torch / DLPack path): all pointers are device memory on the handle's device; the
  * kernels are enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
