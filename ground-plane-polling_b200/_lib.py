@@ -34,6 +34,8 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'gpp_fit_host_multi': (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'gpp_fit_planes_host': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'gpp_fit_host_multi_planes': (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'gpp_fit_device': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

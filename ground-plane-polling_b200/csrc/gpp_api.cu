@@ -460,7 +460,8 @@ struct PoseHost {
 template <class T>
 static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, const int32_t *orient,
                          const float *pinv, int B, int D, T *keypoints, T *keyplanes, T *residuals,
-                         int64_t *best, int mode, const PoseHost &pose = PoseHost()) {
+                         int64_t *best, int mode, const PoseHost &pose = PoseHost(),
+                         const std::function<void()> *while_the_gpu_works = nullptr) {
     if ((long long)B * D == 0) return GPP_OK;
     DeviceGuard guard(h->device);
     // chunk size: enough hypotheses to fill the machine a few times over, at most 65,536 detections
@@ -580,6 +581,7 @@ static int fit_host_impl(gpp_handle *h, const float *boxes, const float *dims, c
                 GPP_CUDA(cudaMemcpyAsync(pose.kitti + 4 * m0, dev + L.o_kitti, sizeof(float) * 4 * nm, cudaMemcpyDeviceToHost, s));
         }
     }
+    if (while_the_gpu_works) (*while_the_gpu_works)();          // everything is enqueued: host work that overlaps it
     if (staged)
         for (int c = (n_chunks > n_streams ? n_chunks - n_streams : 0); c < n_chunks; ++c) {
             int rc = drain(c);
@@ -619,6 +621,45 @@ int gpp_fit_pose_host(gpp_handle *h, const float *boxes, const float *dimensions
     pose.locations = locations; pose.angles = angles; pose.dimensions = dimensions_out; pose.kitti = kitti;
     return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals,
                                 best_index, mode, pose);
+}
+
+// The reference's callers feed the plane database with every image (run_network.py:105, utils/eval.py:91), and one image
+// is a 0.04 ms kernel: the "same database as last time?" comparison (17 us for the 22k database) is the largest host
+// cost of such a call.  Here it runs WHILE the GPU polls against the resident database; if the bytes turn out to differ
+// the database is uploaded and the call polled again (the first results are simply overwritten).  Larger calls, and
+// calls whose database cannot be the resident one (other size / type / order, none resident), take the plain order.
+int gpp_fit_planes_host(gpp_handle *h, const void *planes, int n_planes, int dtype, int order, const float *boxes,
+                        const float *dimensions, const int32_t *orientations, const float *P_inv, int B, int D,
+                        float *keypoints, float *keyplanes, float *residuals, int64_t *best_index, float *locations,
+                        float *angles, float *dimensions_out, float *kitti, int mode) {
+    if (!h || !planes || n_planes <= 0 || dtype < 0 || dtype > 1 || order < 0 || order > 1)
+        return set_error(GPP_EINVAL, "gpp_fit_planes_host: bad plane database argument");
+    if (!float_mode(mode)) return set_error(GPP_EINVAL, "gpp_fit_planes_host: mode %d", mode);
+    const bool with_pose = locations || angles || dimensions_out || kitti;
+    if (with_pose && (long long)B * D > 0 && (!locations || !angles || !dimensions_out))
+        return set_error(GPP_EINVAL, "gpp_fit_planes_host: NULL pose array");
+    PoseHost pose;
+    if (with_pose) { pose.locations = locations; pose.angles = angles; pose.dimensions = dimensions_out; pose.kitti = kitti; }
+    const size_t bytes = (dtype ? sizeof(double) : sizeof(float)) * 4 * (size_t)n_planes;
+    const bool may_be_resident = h->raw_valid && h->n_planes == n_planes && h->raw_dtype == dtype && h->raw_order == order &&
+                                 h->raw_copy.size() == bytes;
+    const bool small = (long long)B * D > 0 && (long long)B * D <= 16384;
+    int rc;
+    if (may_be_resident && small) {
+        rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals, "gpp_fit_planes_host");
+        if (rc) return rc;
+        bool same = true;
+        const std::function<void()> compare = [&] { same = memcmp(h->raw_copy.data(), planes, bytes) == 0; };
+        rc = fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals, best_index,
+                                  mode, pose, &compare);
+        if (rc || same) return rc;
+    }
+    rc = gpp_set_planes_raw(h, planes, n_planes, dtype, order);
+    if (rc) return rc;
+    rc = check_fit_args(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals, "gpp_fit_planes_host");
+    if (rc) return rc;
+    return fit_host_impl<float>(h, boxes, dimensions, orientations, P_inv, B, D, keypoints, keyplanes, residuals, best_index,
+                                mode, pose);
 }
 
 // One caller, several GPUs: the images are split into contiguous shards (the first B % n handles get one image more),

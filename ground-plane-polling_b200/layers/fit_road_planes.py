@@ -82,8 +82,9 @@ class PlanePoller(object):
 
     # ------------------------------------------------------------------ numpy entry
     def fit(self, boxes, dimensions, orientations, P_inv, mode=None, return_index=False, out=None, return_pose=False,
-            return_kitti=False):
-        """fit_road_planes against the resident database.  Returns [keypoints (B, D, 4, 3),
+            return_kitti=False, planes=None):
+        """fit_road_planes against the resident database, or against ``planes`` ((N, 4), as ``set_planes`` takes it: the
+        comparison with the resident database then overlaps the kernel of a small call, gpp_fit_planes_host).  Returns [keypoints (B, D, 4, 3),
         keyplanes (B, D, 1, 4), residuals (B, D)] float32 (float64 in mode 'f64') [+ best index int64]
         [+ locations, angles, dimensions (B, D, 3) with ``return_pose``] [+ KITTI records (B, D, 4) with ``return_kitti``:
         both computed in the polling kernel's epilogue, one launch for everything].
@@ -91,6 +92,15 @@ class PlanePoller(object):
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in _lib.MODES:
             raise ValueError('unknown mode %r (expected one of %s)' % (mode, sorted(_lib.MODES)))
+        if planes is not None:
+            planes = np.asarray(planes)
+            if planes.ndim != 2 or planes.shape[1] != 4 or planes.shape[0] < 1:
+                raise ValueError('planes must have shape (N, 4) with N >= 1, got %r' % (planes.shape,))
+            if planes.dtype not in (np.float32, np.float64) or not (planes.flags['C_CONTIGUOUS'] or planes.flags['F_CONTIGUOUS']):
+                planes = _f32(planes)
+            if mode == 'f64':
+                self.set_planes(planes)
+                planes = None
         boxes = _f32(boxes)
         if boxes.ndim != 3 or boxes.shape[2] != 12:
             raise ValueError('boxes must have shape (B, D, 12), got %r' % (boxes.shape,))
@@ -127,6 +137,16 @@ class PlanePoller(object):
                                  "not available in mode 'f64'")
             pose = [np.empty((B, D, 3), np.float32) for _ in range(3)] + \
                    ([np.empty((B, D, 4), np.float32)] if return_kitti else [None])
+        if planes is not None:
+            p4 = pose if pose is not None else [None] * 4
+            rc = self._lib.gpp_fit_planes_host(self._h, planes.ctypes.data, planes.shape[0], 1 if planes.dtype == np.float64 else 0,
+                                               0 if planes.flags['C_CONTIGUOUS'] else 1, _lib.ptr(boxes), _lib.ptr(dimensions),
+                                               _lib.ptr(orientations), _lib.ptr(P_inv), B, D, _lib.ptr(keypoints),
+                                               _lib.ptr(keyplanes), _lib.ptr(residuals), _lib.ptr(best), _lib.ptr(p4[0]),
+                                               _lib.ptr(p4[1]), _lib.ptr(p4[2]), _lib.ptr(p4[3]), _lib.MODES[mode])
+            _lib.check(rc, 'gpp_fit_planes_host')
+            self._dev_planes = None
+        elif pose is not None:
             rc = self._lib.gpp_fit_pose_host(self._h, _lib.ptr(boxes), _lib.ptr(dimensions), _lib.ptr(orientations),
                                              _lib.ptr(P_inv), B, D, _lib.ptr(keypoints), _lib.ptr(keyplanes),
                                              _lib.ptr(residuals), _lib.ptr(best), _lib.ptr(pose[0]), _lib.ptr(pose[1]),
@@ -364,9 +384,8 @@ def fit_road_planes(boxes, dimensions, orientations, P_inv, planes, mode=None, r
     B = boxes.shape[0]
     groups = _plane_groups(planes, B)
     if len(groups) == 1:
-        poller.set_planes(groups[0][2])
         return poller.fit(boxes, dimensions, orientations, P_inv, mode=mode, return_index=return_index, out=out,
-                          return_pose=return_pose, return_kitti=return_kitti)
+                          return_pose=return_pose, return_kitti=return_kitti, planes=groups[0][2])
     if out is not None:
         raise ValueError('out= is only supported with one plane database shared by the batch')
     dimensions, orientations, P_inv = np.asarray(dimensions), np.asarray(orientations), np.asarray(P_inv)

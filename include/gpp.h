@@ -100,6 +100,16 @@ int gpp_fit_host(gpp_handle *h, const float *boxes, const float *dimensions, con
                  const float *P_inv, int B, int D, float *keypoints, float *keyplanes, float *residuals,
                  int64_t *best_index, int mode);
 
+/* gpp_set_planes_raw + gpp_fit_host (+ the pose / KITTI outputs of gpp_fit_pose_host; all four NULL = none) in one
+ * call, for callers that feed the database with every image like the reference's (run_network.py:105, utils/eval.py:91):
+ * for a small call the "same database as last time?" comparison runs on the host while the GPU already polls against
+ * the resident database, and the call is polled again after an upload if the bytes turn out to differ.  Results are
+ * those of the two separate calls. */
+int gpp_fit_planes_host(gpp_handle *h, const void *planes, int n_planes, int dtype, int order, const float *boxes,
+                        const float *dimensions, const int32_t *orientations, const float *P_inv, int B, int D,
+                        float *keypoints, float *keyplanes, float *residuals, int64_t *best_index, float *locations,
+                        float *angles, float *dimensions_out, float *kitti, int mode);
+
 /* The same call over several GPUs of one box (BASELINE.json configs[3]: images sharded, database replicated, results
  * gathered into one host array): `handles` are n_handles contexts on different devices, each holding the database
  * (gpp_set_planes on every one).  Image shard i -- contiguous, the first B % n_handles shards one image longer -- is

@@ -239,6 +239,29 @@ def test_torch_database_is_never_stale(gpp, poller):
         gpp.fit_road_planes_torch(*t, tiled.contiguous(), mode='exact')
 
 
+def test_database_fed_with_the_call_is_compared_while_the_gpu_polls(gpp, poller):
+    """gpp_fit_planes_host: a small call polls against the resident database while the host compares the bytes it was
+    handed; same bytes -> one launch; other bytes of the same shape -> upload and a second poll, results of the NEW
+    database (also for the pose / KITTI outputs)."""
+    base = load_planes('10k')
+    db1, db2 = np.asfortranarray(base[:3000]), np.asfortranarray(base[3000:6000])           # as loadmat returns them
+    boxes, dims, orient, P_inv = synthetic.synth_detections(1, 100, base, seed=97, n_valid=17)
+    want1 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, db1, return_index=True)
+    want2 = c_oracle.fit_road_planes_c(boxes, dims, orient, P_inv, db2, return_index=True)
+    _assert_identical(gpp.fit_road_planes(boxes, dims, orient, P_inv, db1[None], return_index=True), want1)
+    n0 = poller.launch_count()
+    _assert_identical(gpp.fit_road_planes(boxes, dims, orient, P_inv, db1.copy(order='F')[None], return_index=True), want1)
+    assert poller.launch_count() - n0 == 1                        # the resident database was the right one
+    n0 = poller.launch_count()
+    got = gpp.fit_road_planes(boxes, dims, orient, P_inv, db2[None], return_index=True, return_pose=True, return_kitti=True)
+    _assert_identical(got[:4], want2)
+    assert poller.launch_count() - n0 == 2 + 4                    # polled twice around the upload (4 launches)
+    again = gpp.fit_road_planes(boxes, dims, orient, P_inv, db2[None], return_index=True, return_pose=True, return_kitti=True)
+    for a, b in zip(got, again):
+        assert np.array_equal(a, b, equal_nan=True)
+    _assert_identical(gpp.fit_road_planes(boxes, dims, orient, P_inv, db1[None], mode='exact', return_index=True), want1)
+
+
 def test_large_device_fed_database_gets_the_scan_order(gpp, poller):
     """A database of 32 rows or more that arrives as a CUDA tensor is read back once to derive the order it is scanned
     in (csrc/gpp_order.cu); the results are those of the host-fed database in every mode, on any stream."""
