@@ -97,7 +97,7 @@ int configure_kernels(gpp_handle *h) {
     // scratch of segmented detections: segments are only used below 3 detections per resident warp
     const long long slots = (long long)h->sm_count * kWarps3;
     h->seg_det_cap = 3 * slots;
-    h->seg_items_cap = 6 * slots + 64;
+    h->seg_items_cap = 8 * slots + 64;
     for (int i = 0; i < gpp_handle::kSlots3 && e == cudaSuccess; ++i) {
         gpp_handle::Slot3 &w = h->slot3[i];
         e = cudaMalloc(&w.claim, 2 * sizeof(unsigned long long));
@@ -122,7 +122,7 @@ void release_poll3(gpp_handle *h) {
 }
 
 // Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below three detections per resident warp every
-// detection is cut into plane segments so that the work items still fill the machine about three times over (the
+// detection is cut into plane segments so that the work items fill the machine about five times over (the
 // last wave is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs
 // three times the average -- is long enough to be the tail; at most 24 unless forced).  Tried and dropped (r02): whole
 // rows first and segments only for the last partial wave (64 x 100 x 10k: 0.32 ms against 0.26 ms); two segments for a
@@ -149,7 +149,7 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     const long long n_rows = (io.n_det + det_stride - 1) / det_stride;
     int n_seg = 1;
     if (h->force_seg > 0) n_seg = h->force_seg;
-    else if (n_rows < 3 * slots) n_seg = (int)((3 * slots + n_rows - 1) / n_rows);
+    else if (n_rows < 3 * slots) n_seg = (int)((5 * slots + n_rows - 1) / n_rows);
     if (h->force_seg <= 0 && n_seg > 24) n_seg = 24;      // a single image: 0.038 ms with 24 segments, 0.045 ms with 32
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;

@@ -30,6 +30,9 @@
 #ifndef GPP_LAZY_Z6
 #define GPP_LAZY_Z6 true    /* z_dir_check of the all-six stage 2 is formed only by the rows that get that far (false: at once; measured 17.51 ms against 17.35 ms on C4) */
 #endif
+#ifndef GPP_SEG_MAJOR
+#define GPP_SEG_MAJOR 1
+#endif
 #ifndef GPP_GEN_EXIT
 #define GPP_GEN_EXIT 1      /* general phase: rows leave after the bottom face when no plane can matter (0: measured equal at the
                              benchmark's 1.5 px key-point noise, 4 % / 6 % slower at 4 px / 10 px) */
@@ -789,8 +792,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
         if (item >= n_items) break;                                  // warp-uniform: this warp retires
         if (lane == 0) next_claim = atomicAdd(args.claim, 1ull) + gridDim.x * kWarps;     // claimed one item ahead
         next_claim = __shfl_sync(0xffffffffu, next_claim, 0);
+#if GPP_SEG_MAJOR
+        // Items in segment-major order (segment 0 of every detection, then segment 1, ...; segmented launches have fewer
+        // than 2^32 items): with a few rounds of items per warp, the later segments of a detection start when its first
+        // one has finished, adopt its max-votes and bound before their first row and never enter the general phase.
+        const int seg = kSeg ? int(unsigned(item) / unsigned(n_rows)) : 0;
+        const long long slot = kSeg ? (long long)(unsigned(item) - unsigned(seg) * unsigned(n_rows)) : (long long)item;
+#else
         const long long slot = kSeg ? (long long)(item / (unsigned)n_seg) : (long long)item;   // index into the scratch
         const int seg = kSeg ? int(item - (unsigned long long)slot * (unsigned)n_seg) : 0;
+#endif
         const long long m = slot * stride;
         // a row that repeats the previous row of its image is written by the warp that polls that row
         if (stride == 1 && (m % args.dets_per_image) != 0 && same_detection(args, m, m - 1, lane)) continue;
@@ -857,6 +868,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             if (kVerified) {
                 VerifiedScan sc;
                 sc.begin();
+                if (kSeg && GPP_SEG_MAJOR) sc.adopt(__ldcg(args.seg_best + slot), detx);      // what finished segments found
                 // segments of one detection share their bounds: every fourth row a warp publishes its own (one atomicMax
                 // on the detection's 64-bit key) and adopts the best published so far (one uniform branch per row; the
                 // round-2 profile of C3 showed the per-row form of this exchange at 40 instructions a row)
