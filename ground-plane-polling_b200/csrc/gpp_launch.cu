@@ -96,8 +96,8 @@ int configure_kernels(gpp_handle *h) {
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // scratch of segmented detections: segments are only used below 3 detections per resident warp
     const long long slots = (long long)h->sm_count * kWarps3;
-    h->seg_det_cap = 3 * slots;
-    h->seg_items_cap = 8 * slots + 64;
+    h->seg_det_cap = 4 * slots;
+    h->seg_items_cap = 12 * slots + 64;
     for (int i = 0; i < gpp_handle::kSlots3 && e == cudaSuccess; ++i) {
         gpp_handle::Slot3 &w = h->slot3[i];
         e = cudaMalloc(&w.claim, 2 * sizeof(unsigned long long));
@@ -121,14 +121,15 @@ void release_poll3(gpp_handle *h) {
     }
 }
 
-// Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below three detections per resident warp every
-// detection is cut into plane segments so that the work items fill the machine about five times over (the
-// last wave is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs
-// three times the average -- is long enough to be the tail; at most 24 unless forced).  Tried and dropped (r02): whole
-// rows first and segments only for the last partial wave (64 x 100 x 10k: 0.32 ms against 0.26 ms); two segments for a
-// 512-image shard of an 8-GPU call (2.67 ms against 2.47 ms).  Residency:
-// staging up to 212 KB per SM pays as soon as every warp polls a few items; a call with fewer items than that streams
-// every row from L2 and starts at once.
+// Schedule of one call (see the header of gpp_poll3.cuh).  Segments: below four detections per resident warp every
+// detection is cut into plane segments so that the work items fill the machine about eight times over (the last wave
+// is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs three times
+// the average -- is long enough to be the tail; at least 3, at most 24 unless forced).  Measured with the segment-major
+// item order (kernel ms, verified): 64 x 100 x 10k: 3 segments 0.220, 4: 0.218, 6: 0.213, 8: 0.216; 128 x 100 x 10k: 1: 0.401,
+// 3: 0.372, 4: 0.380; 256 x 100 x 22k: 1: 1.36, 3: 1.34, 4: 1.33; 512 x 100 x 22k: 1: 2.44, 2: 2.60, 3: 2.58 (left whole);
+// a single image: 24: 0.038, 32: 0.045.  Tried and dropped (r02): whole rows first and segments only for the last partial
+// wave (64 x 100 x 10k: 0.32 ms against 0.26 ms).  Residency: staging up to 212 KB per SM pays as soon as every warp polls
+// a few items; a call with fewer items than that streams every row from L2 and starts at once.
 static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride, cudaStream_t s) {
     gpp_handle::Slot3 &w = h->slot3[h->next_slot3++ % gpp_handle::kSlots3];
     cudaError_t e = cudaSuccess;
@@ -149,7 +150,10 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     const long long n_rows = (io.n_det + det_stride - 1) / det_stride;
     int n_seg = 1;
     if (h->force_seg > 0) n_seg = h->force_seg;
-    else if (n_rows < 3 * slots) n_seg = (int)((5 * slots + n_rows - 1) / n_rows);
+    else if (n_rows < 4 * slots) {
+        n_seg = (int)((8 * slots + n_rows / 2) / n_rows);
+        if (n_seg < 3) n_seg = 3;            // two segments were slower than one or three at every size measured
+    }
     if (h->force_seg <= 0 && n_seg > 24) n_seg = 24;      // a single image: 0.038 ms with 24 segments, 0.045 ms with 32
     if (n_seg > 32) n_seg = 32;
     if (n_seg > NR) n_seg = NR;
