@@ -462,10 +462,10 @@ def main():
             poller.set_planes(pl)
             tw = [torch.from_numpy(a).to(dev) for a in (wb, wd, wo, wp)]
             kms, calls = [], []
-            for i in range(8):
+            for i in range(30):                      # sub-millisecond kernels after a database switch: 10 warm-up calls
                 poller.fit_torch(*tw, mode=args.mode)
                 torch.cuda.synchronize()
-                if i:
+                if i >= 10:
                     kms.append(poller.last_kernel_ms())
             feed = np.expand_dims(np.asfortranarray(pl.astype(np.float64)), axis=0)     # the callers' (1, N, 4) float64 feed
             for i in range(30):

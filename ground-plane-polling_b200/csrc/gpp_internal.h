@@ -75,6 +75,8 @@ struct gpp_handle {
         gpp::SegPartial *partials = nullptr;     // [seg_items_cap]
         unsigned int *seg_arrived = nullptr;     // [seg_det_cap]
         unsigned long long *seg_best = nullptr;  // [seg_det_cap]
+        float *seg_consts = nullptr;             // [seg_det_cap][kSharedConsts]
+        unsigned int *seg_ready = nullptr;       // [seg_det_cap]
         cudaEvent_t done = nullptr;
         bool used = false;
     };

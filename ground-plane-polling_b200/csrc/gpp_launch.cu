@@ -107,6 +107,9 @@ int configure_kernels(gpp_handle *h) {
         if (e == cudaSuccess) e = cudaMemset(w.seg_arrived, 0, sizeof(unsigned int) * (size_t)h->seg_det_cap);
         if (e == cudaSuccess) e = cudaMalloc(&w.seg_best, sizeof(unsigned long long) * (size_t)h->seg_det_cap);
         if (e == cudaSuccess) e = cudaMemset(w.seg_best, 0, sizeof(unsigned long long) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMalloc(&w.seg_consts, sizeof(float) * kSharedConsts * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMalloc(&w.seg_ready, sizeof(unsigned int) * (size_t)h->seg_det_cap);
+        if (e == cudaSuccess) e = cudaMemset(w.seg_ready, 0, sizeof(unsigned int) * (size_t)h->seg_det_cap);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) return set_error(GPP_ECUDA, "polling scratch allocation: %s", cudaGetErrorString(e));
@@ -116,6 +119,7 @@ int configure_kernels(gpp_handle *h) {
 void release_poll3(gpp_handle *h) {
     for (auto &w : h->slot3) {
         cudaFree(w.claim); cudaFree(w.partials); cudaFree(w.seg_arrived); cudaFree(w.seg_best);
+        cudaFree(w.seg_consts); cudaFree(w.seg_ready);
         if (w.done) cudaEventDestroy(w.done);
         w = gpp_handle::Slot3();
     }
@@ -144,6 +148,7 @@ static int launch_poll3(gpp_handle *h, const FitIO &io, int mode, int det_stride
     b.pose_kitti = io.pose_locations ? io.pose_kitti : nullptr;
     b.det_stride = det_stride;
     b.claim = w.claim; b.partials = w.partials; b.seg_arrived = w.seg_arrived; b.seg_best = w.seg_best;
+    b.seg_consts = w.seg_consts; b.seg_ready = w.seg_ready;
     const int warps = warps_of(mode);
     const int NR = h->n_pairs_padded / 32;
     const long long slots = (long long)h->sm_count * warps;

@@ -74,6 +74,8 @@ struct PollArgs3 {
     SegPartial *partials;        // [n_det * n_seg]                      (n_seg > 1 only)
     unsigned int *seg_arrived;   // [n_det], zero at launch, reset by the last segment of the detection
     unsigned long long *seg_best;   // [n_det], shared (max-votes, best residual) key of a detection's segments, same life cycle
+    float *seg_consts;           // [n_det][kSharedConsts]: the per-detection constants, written by segment 0 (packed modes)
+    unsigned int *seg_ready;     // [n_det]: seg_consts[slot] is complete; same life cycle
 };
 
 __device__ __forceinline__ Detection<ExactF32> load_det_exact(const float *detx) {
@@ -639,7 +641,8 @@ __device__ __forceinline__ bool same_detection(const PollArgs3 &a, long long m, 
     return __all_sync(0xffffffffu, x == y);
 }
 
-constexpr int kWarpSmem3 = kVerifyQueue * (int)sizeof(int) + 32 * (int)sizeof(float);   // queue + exact / cold constants
+constexpr int kSharedConsts = 40;        // floats of a detection's constant block: [0, 32) the warp's slot, [32, 39) the hot ones
+constexpr int kWarpSmem3 = kVerifyQueue * (int)sizeof(int) + kSharedConsts * (int)sizeof(float);   // queue + constants
 __host__ __device__ constexpr size_t smem3_bytes(int warps, int resident_rows) {
     return size_t(resident_rows) * 1024 + size_t(warps) * kWarpSmem3 + 16;
 }
@@ -808,31 +811,85 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
 
         GPP_TL(tl0);
         // ---- per-detection prologue (warp-uniform), exact arithmetic: fit_road_planes.py:66-72, :80-83
+        // Segments of one detection share it (packed modes): segment 0 leaves the finished constants in the detection's
+        // scratch block, and a later segment that finds them there copies 160 bytes instead of redoing the rays, targets,
+        // square roots and divisions -- with six segments per detection that was a tenth of all instructions of C3.  In
+        // segment-major order segment 0 ran a round earlier; a segment that comes too early just computes them itself.
         Detection<P> detE;
-        load_detection<P, P>(detE, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
-                             args.pinv + 12 * (m / args.dets_per_image));
-        const bool same_rays = same_ground_rays(detE);
+        bool same_rays;
         DetConst D;
-        if constexpr (kPacked) {
-            // the exact constants are only needed by the rare exact paths and the epilogue: parked in shared memory
+        if constexpr (kPacked && kSeg) {
+            __syncwarp();                                                 // the previous item's readers are done
+            if (seg > 0 && __ldcg(args.seg_ready + slot) != 0u) {
+                __threadfence();                                          // the block was complete before the flag was set
+                const float *blk = args.seg_consts + slot * kSharedConsts;
+                detx[lane] = __ldcg(blk + lane);
+                if (lane < kSharedConsts - 32) detx[32 + lane] = __ldcg(blk + 32 + lane);
+            } else {
+                load_detection<P, P>(detE, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
+                                     args.pinv + 12 * (m / args.dets_per_image));
+                DetConst Dw;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) D.td[i] = detE.td[i];
-            fast_constants(D, detE);
-            __syncwarp();                            // the previous item's readers are done
-            if (lane == 0) {
+                for (int i = 0; i < 6; ++i) Dw.td[i] = detE.td[i];
+                fast_constants(Dw, detE);
+                if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    detx[i] = detE.dl[i]; detx[3 + i] = detE.dm[i]; detx[6 + i] = detE.dr[i]; detx[9 + i] = detE.dt[i];
+                    for (int i = 0; i < 3; ++i) {
+                        detx[i] = detE.dl[i]; detx[3 + i] = detE.dm[i]; detx[6 + i] = detE.dr[i]; detx[9 + i] = detE.dt[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) detx[12 + i] = detE.td[i];
+                    store_cold(detx, Dw);
+                    detx[18] = same_ground_rays(detE) ? 1.0f : 0.0f;
+                    detx[32] = Dw.fl[0]; detx[33] = Dw.fl[1]; detx[34] = Dw.fm[0]; detx[35] = Dw.fm[1];
+                    detx[36] = Dw.fr[0]; detx[37] = Dw.fr[1]; detx[38] = Dw.ms;
                 }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) detx[12 + i] = detE.td[i];
-                store_cold(detx, D);
+                if (seg == 0) {
+                    __syncwarp();
+                    float *blk = args.seg_consts + slot * kSharedConsts;
+                    __stcg(blk + lane, detx[lane]);
+                    if (lane < kSharedConsts - 32) __stcg(blk + 32 + lane, detx[32 + lane]);
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) __stcg(args.seg_ready + slot, 1u);
+                }
             }
             __syncwarp();
-            // td[3] comes out of an IEEE square root (a subroutine call the compiler cannot see through): read back from
-            // the warp's slot it is a load from a warp-uniform address, and joins the other hot constants in a uniform
-            // register instead of being reloaded from local memory on every row
-            D.td[3] = detx[15];
+            // Every constant comes out of the warp's slot.  The compiler cannot know that a load from an address derived
+            // from threadIdx gives the same value in all lanes, and would keep the ten hot constants in (spilled) vector
+            // registers: a warp reduction of equal bit patterns returns them in uniform registers, where the scan loops
+            // of the unsegmented kernel have them too.
+            load_cold(D, detx);
+            auto uni = [](float v) { return __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(v))); };
+            D.td[1] = uni(detx[13]); D.td[2] = uni(detx[14]); D.td[3] = uni(detx[15]);
+            D.fl[0] = uni(detx[32]); D.fl[1] = uni(detx[33]); D.fm[0] = uni(detx[34]); D.fm[1] = uni(detx[35]);
+            D.fr[0] = uni(detx[36]); D.fr[1] = uni(detx[37]); D.ms = uni(detx[38]);
+            same_rays = __reduce_or_sync(0xffffffffu, __float_as_uint(detx[18])) != 0u;
+        } else {
+            load_detection<P, P>(detE, args.boxes + 12 * m, args.dims + 3 * m, __ldg(args.orient + m),
+                                 args.pinv + 12 * (m / args.dets_per_image));
+            same_rays = same_ground_rays(detE);
+            if constexpr (kPacked) {
+                // the exact constants are only needed by the rare exact paths and the epilogue: parked in shared memory
+#pragma unroll
+                for (int i = 0; i < 6; ++i) D.td[i] = detE.td[i];
+                fast_constants(D, detE);
+                __syncwarp();                            // the previous item's readers are done
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        detx[i] = detE.dl[i]; detx[3 + i] = detE.dm[i]; detx[6 + i] = detE.dr[i]; detx[9 + i] = detE.dt[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) detx[12 + i] = detE.td[i];
+                    store_cold(detx, D);
+                }
+                __syncwarp();
+                // td[3] comes out of an IEEE square root (a subroutine call the compiler cannot see through): read back
+                // from the warp's slot it is a load from a warp-uniform address, and joins the other hot constants in a
+                // uniform register instead of being reloaded from local memory on every row
+                D.td[3] = detx[15];
+            }
         }
 
         GPP_TL(tl1);
@@ -934,6 +991,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) poll3_kernel(const PollArgs3 a
             if (lane == 0) {                          // leave the scratch as it was found
                 args.seg_arrived[slot] = 0u;
                 args.seg_best[slot] = 0ull;
+                args.seg_ready[slot] = 0u;
             }
         }
 
