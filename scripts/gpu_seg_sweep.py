@@ -15,7 +15,7 @@ poller = gpp_b200.get_poller(0)
 CASES = ((64, '10k'), (16, '22k'), (4, '22k'), (1, '22k'), (128, '10k'))
 if len(sys.argv) > 1:          # e.g. 512:22k 256:22k
     CASES = tuple((int(a.split(':')[0]), a.split(':')[1]) for a in sys.argv[1:])
-SEGS = (0, 4, 5, 6, 7, 8) if len(sys.argv) > 1 else (0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
+SEGS = (0, 5, 6, 7, 8) if len(sys.argv) > 1 else (0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
 for B, tag in CASES:
     pl = np.load(os.path.join(ROOT, 'road_planes_database', 'road_planes_database_%s.npy' % tag))
     boxes, dims, orient, P_inv = synthetic.synth_detections(B, 100, pl, seed=11)
