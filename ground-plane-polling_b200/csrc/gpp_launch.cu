@@ -130,7 +130,8 @@ void release_poll3(gpp_handle *h) {
 // is then short whatever the batch size, and no single item -- a detection without a six-vote plane costs three times
 // the average -- is long enough to be the tail; at least 3, at most 24 unless forced).  Measured with the segment-major
 // item order (kernel ms, verified): 64 x 100 x 10k: 3 segments 0.220, 4: 0.218, 6: 0.213, 8: 0.216; 128 x 100 x 10k: 1: 0.401,
-// 3: 0.372, 4: 0.380; 256 x 100 x 22k: 1: 1.36, 3: 1.34, 4: 1.33; 512 x 100 x 22k: 1: 2.44, 2: 2.60, 3: 2.58 (left whole);
+// 3: 0.372, 4: 0.380; 256 x 100 x 22k: 1: 1.35, 3: 1.35, 4: 1.31; 384 x 100 x 22k: 1: 1.88, 3: 1.95; 512 x 100 x 22k: 1: 2.44,
+// 2: 2.60, 3: 2.58, 4: 2.55 (with the shared constants; left whole from four detections per warp on);
 // a single image: 24: 0.038, 32: 0.045.  Tried and dropped (r02): whole rows first and segments only for the last partial
 // wave (64 x 100 x 10k: 0.32 ms against 0.26 ms).  Residency: staging up to 212 KB per SM pays as soon as every warp polls
 // a few items; a call with fewer items than that streams every row from L2 and starts at once.
