@@ -704,7 +704,7 @@ __device__ __forceinline__ void scalar_scan(const Detection<P> &det, const typen
         const T4 pl = planes[valid ? p : n_planes - 1];
         T X[4][3];
         int V; T R; bool zneg;
-        if (Mw >= 5) {
+        if (Mw >= (sizeof(T) == 8 ? 6 : 5)) {          // (the fp64 scan, in index order, is faster staged from 6 only)
             T rb[3];
             rb[2] = bottom_lr<Q>(dq, pl.x, pl.y, pl.z, pl.w, X);
             if (!__any_sync(0xffffffffu, valid && (!(rb[2] > wbest) || (Mw == 5 && !(rb[2] > thr))))) continue;
