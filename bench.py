@@ -527,7 +527,10 @@ def main():
                          'fma_pipe_active_pct': pipes['fma_pipe_active_pct'] if pipes else None,
                          'xu_pipe_pct': pipes['xu_pipe_pct'] if pipes else None,
                          'issue_active_pct': pipes['issue_active_pct'] if pipes else None,
-                         'pipe_source': pipes['source'] if pipes else None},
+                         'pipe_source': pipes['source'] if pipes else None,
+                         'frac_note': 'achieved counts the ALGORITHMIC 148 FLOP of every hypothesis (SURVEY.md 8.4); the kernel '
+                                      'drops most rows of 64 planes after less than half a hypothesis, so frac can exceed 1 -- '
+                                      'how busy the pipes are is fma_pipe_active_pct / xu_pipe_pct / issue_active_pct'},
             'cpu_baseline': cpu,
             'other_modes': dict(other_modes, unit=UNIT),
             'other_workloads': other_workloads,
